@@ -1,0 +1,204 @@
+/* libmxdet_sm100.so - C ABI of the B200-native detection hot path.
+ *
+ * Drop-in boundary for the data-parallel hot path of jiangzhengkai/mxdetection
+ * (SURVEY.md section 8b).  The mounted reference holds no source, so each
+ * entry cites the README line of the module it serves and the MXNet 1.3 /
+ * mmdetection-0.5 operator whose contract it implements.
+ *
+ * Conventions
+ *  - Tensors cross as `const DLTensor*` (borrowed; see mxdet_dlpack.h).  They
+ *    must live on ONE CUDA device (kDLCUDA / kDLCUDAManaged), be compact
+ *    row-major (strides NULL or canonical) and have exactly the dtype stated.
+ *    A CPU tensor is refused with MXD_ENOTSUP: there is no CPU fallback.
+ *  - The caller owns every input, output and workspace.  The library never
+ *    allocates, frees or synchronises; every call only enqueues kernels on
+ *    `stream` (a cudaStream_t passed as void*, NULL = legacy default stream)
+ *    and is CUDA-graph capturable.
+ *  - Outputs of data-dependent length have fixed capacity plus a device
+ *    int32 count.
+ *  - Return value 0 (MXD_OK) or a negative MXD_E* code; the message is in
+ *    the thread-local mxd_last_error().  Re-entrant; no global mutable state
+ *    other than the error string and the launch counter.
+ *  - delta ("legacy +1"): 1.0 for the py-faster-rcnn / mmdet-0.5 lineage
+ *    (widths x2-x1+1), 0.0 for mx.nd.contrib.box_nms / box_iou.
+ *  - All IoU / threshold / label arithmetic is fp32 round-to-nearest without
+ *    FMA contraction, in the order of SURVEY.md 8(a) Specs A-H.
+ */
+#ifndef MXDET_H_
+#define MXDET_H_
+#include <stddef.h>
+#include <stdint.h>
+#include "mxdet_dlpack.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MXD_OK 0
+#define MXD_EINVAL (-1)     /* bad shape / dtype / stride / attribute            */
+#define MXD_ENOTSUP (-2)    /* CPU tensor, or size outside the supported range   */
+#define MXD_ECUDA (-3)      /* CUDA runtime error at enqueue time                */
+#define MXD_EWORKSPACE (-4) /* workspace NULL or too small                       */
+
+#define MXD_MAX_LEVELS 8    /* FPN levels per call                               */
+#define MXD_MAX_BASE_ANCHORS 16
+#define MXD_SORT_CAP 8192   /* max rows sorted inside one CTA (top-k / NMS)      */
+
+/* ---- library ------------------------------------------------------------ */
+int mxd_version(void);                /* 10000*major + 100*minor + patch        */
+const char* mxd_last_error(void);     /* thread-local, valid until next call    */
+uint64_t mxd_launch_count(void);      /* kernels enqueued by this library so far */
+
+/* ---- A1/A2  RoIAlign  (mxdetection/ops, /root/reference/README.md:24;
+ *      contract mx.nd.contrib.ROIAlign + _backward_ROIAlign, mxnet 1.3.0
+ *      /root/reference/README.md:37; Spec A) -------------------------------- */
+/* data (N,C,H,W) f32; rois (R,5) f32 [b,x1,y1,x2,y2]; out (R,C,PH,PW) f32.     */
+int mxd_roi_align_forward(const DLTensor* data, const DLTensor* rois, DLTensor* out,
+                          int pooled_h, int pooled_w, float spatial_scale, int sample_ratio,
+                          void* stream);
+/* grad_out (R,C,PH,PW); grad_data (N,C,H,W).  accumulate=0: req='write'
+ * (grad_data is zero-filled first); accumulate=1: req='add'.  grad wrt rois is
+ * identically zero and not produced.                                            */
+int mxd_roi_align_backward(const DLTensor* grad_out, const DLTensor* rois, DLTensor* grad_data,
+                           int pooled_h, int pooled_w, float spatial_scale, int sample_ratio,
+                           int accumulate, void* stream);
+
+/* ---- G1/G2  FPN level assignment + multi-level RoI extraction
+ *      (mxdetection/models/roi_extractors, /root/reference/README.md:32;
+ *      SingleLevelRoI.map_roi_levels / .forward of mmdet 0.5; Spec G) -------- */
+/* rois (R,5) or (R,4) f32 -> levels (R) i32.                                   */
+int mxd_map_roi_levels(const DLTensor* rois, DLTensor* levels, int num_levels,
+                       float finest_scale, void* stream);
+/* feats[l] (N,C,H_l,W_l) f32; levels (R) i32 or NULL (then Spec G is evaluated
+ * in-kernel with finest_scale); spatial_scales host float[num_levels].          */
+int mxd_roi_align_fpn_forward(const DLTensor* const* feats, int num_levels,
+                              const float* spatial_scales, const DLTensor* rois,
+                              const DLTensor* levels, DLTensor* out,
+                              int pooled_h, int pooled_w, int sample_ratio, float finest_scale,
+                              void* stream);
+int mxd_roi_align_fpn_backward(const DLTensor* grad_out, const DLTensor* rois,
+                               const DLTensor* levels, DLTensor* const* grad_feats,
+                               int num_levels, const float* spatial_scales,
+                               int pooled_h, int pooled_w, int sample_ratio, float finest_scale,
+                               int accumulate, void* stream);
+
+/* ---- B1  NMS  (mxdetection/ops, /root/reference/README.md:24; contract
+ *      mx.nd.contrib.box_nms, Spec B: strict iou > thr, stable score-desc /
+ *      index-asc order) ---------------------------------------------------- */
+/* Stable top-k: scores (S,n) f32 -> idx (S,k) i32, vals (S,k) f32 sorted by
+ * (score desc, index asc); k = min(topk,n) (topk<=0: k=n).  Needs k <=
+ * MXD_SORT_CAP.                                                               */
+size_t mxd_topk_stable_workspace_bytes(int segments, int n, int topk);
+int mxd_topk_stable(const DLTensor* scores, DLTensor* idx, DLTensor* vals, int topk,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* boxes (n,4), scores (n) f32; ids (n) i32 or NULL; keep (cap) i32 receives
+ * original row indices in score order, num_keep (1) i32 the count
+ * (min(kept,cap)).  Rows with score <= valid_thresh are dropped first (pass
+ * -INFINITY to keep all); topk<=0 = all; max_out<=0 = unlimited.
+ * force_suppress=0 suppresses only rows with equal ids.                         */
+size_t mxd_nms_workspace_bytes(int n, int topk);
+int mxd_nms(const DLTensor* boxes, const DLTensor* scores, const DLTensor* ids,
+            DLTensor* keep, DLTensor* num_keep, float iou_thr, float delta, int topk,
+            float valid_thresh, int force_suppress, int max_out,
+            void* workspace, size_t workspace_bytes, void* stream);
+/* MXNet tensor form: data (B,N,K) f32 -> out (B,N,K) kept rows first (score
+ * order), all other rows -1; index (B,N) i32 or NULL receives the source row of
+ * each output row (-1 for padding) - the record box_nms' backward consumes.
+ * in_format/out_format: 0 corner, 1 center.                                      */
+size_t mxd_box_nms_workspace_bytes(int batch, int n, int topk);
+int mxd_box_nms(const DLTensor* data, DLTensor* out, DLTensor* index, float overlap_thresh,
+                float valid_thresh, int topk, int coord_start, int score_index, int id_index,
+                int force_suppress, int in_format, int out_format,
+                void* workspace, size_t workspace_bytes, void* stream);
+/* _backward_box_nms: in_grad[b,index[b,r],:] = out_grad[b,r,:], zero elsewhere. */
+int mxd_box_nms_backward(const DLTensor* out_grad, const DLTensor* index, DLTensor* in_grad,
+                         void* stream);
+
+/* ---- C1/C2  anchors  (mxdetection/core/anchor, /root/reference/README.md:16;
+ *      AnchorGenerator.grid_anchors / valid_flags, anchor_inside_flags of
+ *      mmdet 0.5; Spec C) -------------------------------------------------- */
+/* base_anchors: host float[num_base*4]; out (feat_h*feat_w*num_base, 4) f32,
+ * order (y,x,a).                                                               */
+int mxd_grid_anchors(const float* base_anchors, int num_base, int feat_h, int feat_w,
+                     float stride, DLTensor* out, void* stream);
+/* flags (feat_h*feat_w*num_base) u8: cell valid iff y<valid_h && x<valid_w.     */
+int mxd_valid_flags(int feat_h, int feat_w, int valid_h, int valid_w, int num_base,
+                    DLTensor* flags, void* stream);
+/* out = valid & x1>=-ab & y1>=-ab & x2<img_w+ab & y2<img_h+ab (ab<0: = valid).  */
+int mxd_inside_flags(const DLTensor* anchors, const DLTensor* valid, int img_h, int img_w,
+                     float allowed_border, DLTensor* out, void* stream);
+
+/* ---- D1/D2  IoU + max-IoU assigner  (mxdetection/core/bbox and core/anchor,
+ *      /root/reference/README.md:16-17; bbox_overlaps /
+ *      bbox_assign_wrt_overlaps of mmdet 0.5, mx.nd.contrib.box_iou; Specs D,E) */
+/* b1 (G,4), b2 (N,4) -> out (G,N) f32 (materialising; tests and small G*N).     */
+int mxd_bbox_overlaps(const DLTensor* b1, const DLTensor* b2, DLTensor* out, float delta,
+                      void* stream);
+/* Fused (never materialises G x N).  anchors (N,4); gts (B,G,4) [or (G,4), B=1];
+ * num_gts (B) i32 or NULL (= G each); gt_labels (B,G) i32 or NULL; flags (N) or
+ * (B,N) u8 or NULL.  Outputs (B,N): assigned i32 (-1 ignore, 0 neg, g+1 pos),
+ * max_overlaps f32, labels i32 (or NULL).                                        */
+size_t mxd_max_iou_assign_workspace_bytes(int batch, int num_gt);
+int mxd_max_iou_assign(const DLTensor* anchors, const DLTensor* gts, const DLTensor* num_gts,
+                       const DLTensor* gt_labels, const DLTensor* flags,
+                       DLTensor* assigned, DLTensor* max_overlaps, DLTensor* labels,
+                       float pos_iou_thr, float neg_iou_thr, float min_pos_iou, float delta,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- F1/F2  delta encode / decode + clip  (mxdetection/core/bbox,
+ *      /root/reference/README.md:17; bbox2delta / delta2bbox of mmdet 0.5;
+ *      Spec F).  means/stds: host float[4].  exp/log correctly rounded fp32.   */
+int mxd_bbox2delta(const DLTensor* proposals, const DLTensor* gts, DLTensor* deltas,
+                   const float* means, const float* stds, void* stream);
+/* max_h/max_w <= 0: no clipping.                                               */
+int mxd_delta2bbox(const DLTensor* rois, const DLTensor* deltas, DLTensor* boxes,
+                   const float* means, const float* stds, int max_h, int max_w,
+                   double wh_ratio_clip, void* stream);
+
+/* ---- H1  RPN proposal stage  (mxdetection/models/rpn_heads,
+ *      /root/reference/README.md:28; RPNHead.get_proposals of mmdet 0.5 /
+ *      mx.nd.contrib.MultiProposal; Spec H) -------------------------------- */
+typedef struct {
+  int num_levels;
+  int feat_h[MXD_MAX_LEVELS];
+  int feat_w[MXD_MAX_LEVELS];
+  float stride[MXD_MAX_LEVELS];
+  int num_base;                                         /* A, same on every level */
+  float base_anchors[MXD_MAX_LEVELS][MXD_MAX_BASE_ANCHORS][4];
+  int nms_pre;          /* per-level pre-NMS top-k (<=0: all)                    */
+  int nms_post;         /* per-level post-NMS cap                                */
+  int max_num;          /* per-image output rows                                 */
+  float nms_thr;
+  float min_bbox_size;  /* <=0: no filter                                        */
+  float means[4];
+  float stds[4];
+  float delta;          /* 1.0                                                   */
+  double wh_ratio_clip; /* 16/1000 (double: |log| is rounded to fp32 once)       */
+} mxd_rpn_config;
+/* scores[l] (B, H_l*W_l*A) f32 activated, (y,x,a) order; deltas[l]
+ * (B, H_l*W_l*A, 4) f32; img_shapes (B,2) i32 [h,w] on device;
+ * proposals (B,max_num,5) f32 [x1,y1,x2,y2,score] zero padded; num_valid (B) i32. */
+size_t mxd_rpn_proposals_workspace_bytes(const mxd_rpn_config* cfg, int batch);
+/* kmax = max_l min(nms_pre, n_l) (row stride of the per-segment stage buffers),
+ * keep_stride = min(nms_post, kmax).                                            */
+/* sizeof(mxd_rpn_config) as compiled into the library (binding self-check).       */
+int mxd_sizeof_rpn_config(void);
+int mxd_rpn_proposals_dims(const mxd_rpn_config* cfg, int* kmax, int* keep_stride);
+int mxd_rpn_proposals(const DLTensor* const* scores, const DLTensor* const* deltas,
+                      const DLTensor* img_shapes, const mxd_rpn_config* cfg,
+                      DLTensor* proposals, DLTensor* num_valid,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* Stage-wise outputs of the last mxd_rpn_proposals call that used `workspace`
+ * (for the stage-wise parity tests): copies, per (image b, level l) segment,
+ * the sorted top-k indices / decoded boxes / keep positions into caller
+ * buffers.  idx (B,L,kmax) i32 (-1 padded); boxes (B,L,kmax,4) f32;
+ * keep (B,L,keep_stride) i32 positions into the sorted rows (-1 padded);
+ * counts (B,L,2) i32 [n_sorted,n_keep].                                         */
+int mxd_rpn_proposals_stages(const mxd_rpn_config* cfg, int batch, const void* workspace,
+                             size_t workspace_bytes, DLTensor* idx, DLTensor* boxes,
+                             DLTensor* keep, DLTensor* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MXDET_H_ */

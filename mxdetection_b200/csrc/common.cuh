@@ -1,0 +1,130 @@
+// Shared helpers for libmxdet_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <math.h>
+#include "../../include/mxdet.h"
+
+namespace mxd {
+
+// ---- error plumbing ---------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define MXD_REQUIRE(cond, code, ...)                 \
+  do {                                               \
+    if (!(cond)) return ::mxd::set_error((code), __VA_ARGS__); \
+  } while (0)
+
+#define MXD_CUDA_OK(expr)                                                        \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess)                                                       \
+      return ::mxd::set_error(MXD_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+// Call after every kernel launch: counts it and surfaces launch-config errors.
+#define MXD_POST_LAUNCH(name)                                                    \
+  do {                                                                           \
+    ::mxd::count_launch();                                                       \
+    cudaError_t _e = cudaPeekAtLastError();                                      \
+    if (_e != cudaSuccess) {                                                     \
+      cudaGetLastError();                                                        \
+      return ::mxd::set_error(MXD_ECUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+    }                                                                            \
+  } while (0)
+
+// ---- DLTensor validation ------------------------------------------------------
+enum DT { F32, I32, U8 };
+
+inline bool dtype_is(const DLTensor* t, DT d) {
+  if (t->dtype.lanes != 1) return false;
+  switch (d) {
+    case F32: return t->dtype.code == kDLFloat && t->dtype.bits == 32;
+    case I32: return t->dtype.code == kDLInt && t->dtype.bits == 32;
+    case U8:  return (t->dtype.code == kDLUInt || t->dtype.code == kDLBool) && t->dtype.bits == 8;
+  }
+  return false;
+}
+
+inline bool is_compact(const DLTensor* t) {
+  if (!t->strides) return true;
+  int64_t s = 1;
+  for (int i = t->ndim - 1; i >= 0; --i) {
+    if (t->shape[i] != 1 && t->strides[i] != s) return false;
+    s *= t->shape[i];
+  }
+  return true;
+}
+
+inline int64_t numel(const DLTensor* t) {
+  int64_t n = 1;
+  for (int i = 0; i < t->ndim; ++i) n *= t->shape[i];
+  return n;
+}
+
+// Validates device / dtype / rank / contiguity; *dev tracks the common device.
+int check_tensor(const DLTensor* t, const char* name, DT dt, int ndim_lo, int ndim_hi, int* dev);
+
+template <typename T>
+inline T* dptr(const DLTensor* t) {
+  return reinterpret_cast<T*>(static_cast<char*>(t->data) + t->byte_offset);
+}
+
+inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- device helpers -------------------------------------------------------------
+// float -> uint32 whose unsigned order equals the float order (-0 == +0).
+__device__ __forceinline__ uint32_t f32_orderable(float x) {
+  uint32_t u = __float_as_uint(__fadd_rn(x, 0.0f));
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_orderable(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+// Spec B / Spec D intersection-over-union pieces, strict fp32, no contraction.
+__device__ __forceinline__ float box_area_clamped(float x1, float y1, float x2, float y2, float d) {
+  float w = fmaxf(__fadd_rn(__fsub_rn(x2, x1), d), 0.0f);
+  float h = fmaxf(__fadd_rn(__fsub_rn(y2, y1), d), 0.0f);
+  return __fmul_rn(w, h);
+}
+__device__ __forceinline__ float box_area_raw(float x1, float y1, float x2, float y2, float d) {
+  return __fmul_rn(__fadd_rn(__fsub_rn(x2, x1), d), __fadd_rn(__fsub_rn(y2, y1), d));
+}
+// Returns true and sets iou when the boxes intersect with positive iw, ih.
+__device__ __forceinline__ bool box_iou_pos(const float4& a, float area_a, const float4& b,
+                                            float area_b, float d, float* iou) {
+  float iw = __fadd_rn(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), d);
+  float ih = __fadd_rn(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), d);
+  if (!(iw > 0.0f) || !(ih > 0.0f)) return false;
+  float inter = __fmul_rn(iw, ih);
+  *iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return true;
+}
+
+// Correctly rounded fp32 exp/log (fp64 evaluation, one rounding) - Spec F.
+__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ float log_cr(float x) { return (float)log((double)x); }
+
+// Spec G canonical threshold form.
+__device__ __forceinline__ int roi_level(float x1, float y1, float x2, float y2, int num_levels,
+                                         float finest_scale) {
+  float w = __fadd_rn(__fsub_rn(x2, x1), 1.0f), h = __fadd_rn(__fsub_rn(y2, y1), 1.0f);
+  float s = __fsqrt_rn(__fmul_rn(w, h));
+  float v = __fadd_rn(__fdiv_rn(s, finest_scale), 1e-6f);
+  int lvl = 0;
+  float t = 2.0f;
+  for (int i = 1; i < num_levels; ++i) {
+    lvl += (v >= t) ? 1 : 0;
+    t = __fmul_rn(t, 2.0f);
+  }
+  return lvl;
+}
+
+}  // namespace mxd

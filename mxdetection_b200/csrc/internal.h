@@ -1,0 +1,101 @@
+// Host-side launchers shared between translation units of libmxdet_sm100.so.
+#pragma once
+#include "common.cuh"
+
+namespace mxd {
+
+// ---- stable top-k (+ optional fused anchor regeneration / delta decode) -------
+struct TopkParams {
+  int num_levels;                       // segments s = b * num_levels + l
+  int batch;
+  const float* scores[MXD_MAX_LEVELS];  // element i of segment (b,l): scores[l][b*seg_stride[l] + i*elem_stride]
+  long long seg_stride[MXD_MAX_LEVELS];
+  int elem_stride;
+  int n[MXD_MAX_LEVELS];
+  int k[MXD_MAX_LEVELS];                // min(topk, n) per level, <= MXD_SORT_CAP
+  int kmax;                             // row stride of the outputs
+  float valid_thresh;                   // rows with score <= valid_thresh are dropped (-inf: none)
+  int* out_idx;                         // (S,kmax) i32, -1 padded
+  float* out_val;                       // (S,kmax) f32 or null
+  int* out_cnt;                         // (S) i32 or null: number of real rows
+  // fused decode (Spec F on regenerated anchors, Spec C) -- enabled when out_boxes != null
+  float4* out_boxes;                    // (S,kmax)
+  uint8_t* out_valid;                   // (S,kmax) min-size flag
+  const float* deltas[MXD_MAX_LEVELS];  // (B, n_l, 4)
+  int feat_w[MXD_MAX_LEVELS];
+  float stride[MXD_MAX_LEVELS];
+  int num_base;
+  float base[MXD_MAX_LEVELS][MXD_MAX_BASE_ANCHORS][4];
+  const int* img_shapes;                // (B,2) [h,w]
+  float means[4], stds[4];
+  float max_ratio;
+  float min_size;
+};
+int launch_topk(const TopkParams& p, cudaStream_t st);
+
+// ---- NMS over score-sorted segments ---------------------------------------------
+struct NmsSortedArgs {
+  const float4* boxes;     // [S][stride], score-descending inside each segment
+  const uint8_t* valid;    // [S][stride] or null
+  const int* ids;          // [S][stride] or null => class-agnostic
+  const int* counts;       // [S] rows per segment, or null => n_max
+  const int* order;        // [S][stride] or null: keep[] = order[pos] instead of pos
+  int S, stride, n_max;
+  float thr, delta;
+  int max_out;             // <=0: unlimited
+  unsigned long long* mask;  // workspace, nms_mask_words(S, n_max) u64
+  int* keep;               // [S][keep_stride], -1 padded
+  int keep_stride;
+  int* keep_cnt;           // [S]
+};
+size_t nms_mask_words(int S, int n_max);
+int launch_nms_sorted(const NmsSortedArgs& a, cudaStream_t st);
+
+// Spec F decode of one box (strict fp32, correctly rounded exp).
+__device__ __forceinline__ float4 decode_box(float4 r, float4 dl, const float* means, const float* stds,
+                                             float max_ratio, float hmax, float wmax, bool clip) {
+  float dx = __fadd_rn(__fmul_rn(dl.x, stds[0]), means[0]);
+  float dy = __fadd_rn(__fmul_rn(dl.y, stds[1]), means[1]);
+  float dw = __fadd_rn(__fmul_rn(dl.z, stds[2]), means[2]);
+  float dh = __fadd_rn(__fmul_rn(dl.w, stds[3]), means[3]);
+  dw = fminf(fmaxf(dw, -max_ratio), max_ratio);
+  dh = fminf(fmaxf(dh, -max_ratio), max_ratio);
+  float px = __fmul_rn(__fadd_rn(r.x, r.z), 0.5f), py = __fmul_rn(__fadd_rn(r.y, r.w), 0.5f);
+  float pw = __fadd_rn(__fsub_rn(r.z, r.x), 1.0f), ph = __fadd_rn(__fsub_rn(r.w, r.y), 1.0f);
+  float gw = __fmul_rn(pw, exp_cr(dw)), gh = __fmul_rn(ph, exp_cr(dh));
+  float gx = __fadd_rn(px, __fmul_rn(pw, dx)), gy = __fadd_rn(py, __fmul_rn(ph, dy));
+  float4 o;
+  o.x = __fadd_rn(__fsub_rn(gx, __fmul_rn(gw, 0.5f)), 0.5f);
+  o.y = __fadd_rn(__fsub_rn(gy, __fmul_rn(gh, 0.5f)), 0.5f);
+  o.z = __fsub_rn(__fadd_rn(gx, __fmul_rn(gw, 0.5f)), 0.5f);
+  o.w = __fsub_rn(__fadd_rn(gy, __fmul_rn(gh, 0.5f)), 0.5f);
+  if (clip) {
+    o.x = fminf(fmaxf(o.x, 0.0f), wmax); o.z = fminf(fmaxf(o.z, 0.0f), wmax);
+    o.y = fminf(fmaxf(o.y, 0.0f), hmax); o.w = fminf(fmaxf(o.w, 0.0f), hmax);
+  }
+  return o;
+}
+
+// Block-wide bitonic sort of P (power of two) u64 keys in shared memory, DESCENDING.
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int P) {
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if ((a < b) == up) { keys[lo] = b; keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace mxd

@@ -1,0 +1,376 @@
+// Hard NMS (Spec B): 64-bit suppression bitmask + single-warp greedy resolve.
+//
+// Contract: mx.nd.contrib.box_nms of mxnet 1.3.0 (module mxdetection/ops,
+// /root/reference/README.md:24): stable score-descending order, strict
+// `iou > thr`, optional class ids / force_suppress, keep indices in score order.
+//
+// Kernel 1 (mask): grid (col block, row block, segment), 64 threads.  Thread r
+//   of a row block tests its box against the 64 boxes of the column block held
+//   in shared memory and writes one u64 word.  Only the upper triangle runs.
+// Kernel 2 (resolve): one warp per segment.  For each block of 64 boxes the
+//   diagonal words are resolved sequentially with shuffles (all lanes track
+//   the same `cur` word), then the rows of the kept boxes are OR-ed into the
+//   per-lane remaining-suppression words; nothing leaves the device (MXNet's
+//   MultiProposal copies the mask to the host for this step).
+#include "internal.h"
+
+namespace mxd {
+
+typedef unsigned long long u64;
+
+__global__ void __launch_bounds__(64) nms_mask_kernel(NmsSortedArgs a, int W) {
+  const int cb = blockIdx.x, rb = blockIdx.y, s = blockIdx.z;
+  if (cb < rb) return;
+  const int n = a.counts ? min(a.counts[s], a.n_max) : a.n_max;
+  if (rb * 64 >= n || cb * 64 >= n) return;
+  const size_t seg = (size_t)s * a.stride;
+  __shared__ float4 sb[64];
+  __shared__ float sa[64];
+  __shared__ int sid[64];
+  const int t = threadIdx.x;
+  const int c = cb * 64 + t;
+  if (c < n) {
+    float4 b = a.boxes[seg + c];
+    sb[t] = b;
+    sa[t] = box_area_clamped(b.x, b.y, b.z, b.w, a.delta);
+    sid[t] = a.ids ? a.ids[seg + c] : 0;
+  }
+  __syncthreads();
+  const int r = rb * 64 + t;
+  if (r >= n) return;
+  const float4 me = a.boxes[seg + r];
+  const float area = box_area_clamped(me.x, me.y, me.z, me.w, a.delta);
+  const int myid = a.ids ? a.ids[seg + r] : 0;
+  const int ncol = min(64, n - cb * 64);
+  u64 bits = 0;
+  const int start = (cb == rb) ? t + 1 : 0;  // strictly later boxes only
+  for (int i = start; i < ncol; ++i) {
+    if (sid[i] != myid) continue;
+    float iou;
+    if (box_iou_pos(me, area, sb[i], sa[i], a.delta, &iou) && iou > a.thr) bits |= 1ull << i;
+  }
+  a.mask[((size_t)s * a.n_max + r) * W + cb] = bits;
+}
+
+__global__ void __launch_bounds__(32) nms_resolve_kernel(NmsSortedArgs a, int W) {
+  extern __shared__ u64 remv[];  // W words
+  const int s = blockIdx.x;
+  const int lane = threadIdx.x;
+  const int n = a.counts ? min(a.counts[s], a.n_max) : a.n_max;
+  const int nW = (n + 63) >> 6;
+  const size_t seg = (size_t)s * a.stride;
+  const u64* __restrict__ mask = a.mask + (size_t)s * a.n_max * W;
+  int* keep = a.keep + (size_t)s * a.keep_stride;
+  const int cap = (a.max_out > 0) ? min(a.max_out, a.keep_stride) : a.keep_stride;
+  for (int w = lane; w < nW; w += 32) remv[w] = 0;
+  __syncwarp();
+  int nkeep = 0;
+  bool done = false;
+  for (int j = 0; j < nW && !done; ++j) {
+    const int r0 = j * 64 + lane, r1 = r0 + 32;
+    // rows past n and rows failing the min-size filter start out suppressed
+    const bool dead0 = r0 >= n || (a.valid && !a.valid[seg + r0]);
+    const bool dead1 = r1 >= n || (a.valid && !a.valid[seg + r1]);
+    u64 cur = remv[j] | (u64)__ballot_sync(0xffffffffu, dead0) | ((u64)__ballot_sync(0xffffffffu, dead1) << 32);
+    const u64 wlo = (r0 < n) ? mask[(size_t)r0 * W + j] : 0ull;
+    const u64 whi = (r1 < n) ? mask[(size_t)r1 * W + j] : 0ull;
+    u64 keepbits = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      const u64 wi = __shfl_sync(0xffffffffu, i < 32 ? wlo : whi, i & 31);
+      if (!((cur >> i) & 1ull)) {
+        keepbits |= 1ull << i;
+        cur |= wi;
+      }
+    }
+    int c = __popcll(keepbits);
+    if (nkeep + c >= cap) {  // trim to the first (cap - nkeep) kept boxes
+      int extra = nkeep + c - cap;
+      while (extra-- > 0) keepbits &= ~(1ull << (63 - __clzll(keepbits)));
+      c = cap - nkeep;
+      done = true;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int bit = lane + 32 * half;
+      if ((keepbits >> bit) & 1ull) {
+        const int pos = nkeep + __popcll(keepbits & ((1ull << bit) - 1ull));
+        const int row = j * 64 + bit;
+        keep[pos] = a.order ? a.order[seg + row] : row;
+      }
+    }
+    nkeep += c;
+    if (done) break;
+    for (int w = j + 1 + lane; w < nW; w += 32) {
+      u64 acc = remv[w];
+      u64 kb = keepbits;
+      while (kb) {
+        u64 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = 0;
+          if (kb) {
+            const int i = __ffsll((long long)kb) - 1;
+            kb &= kb - 1;
+            v[u] = mask[(size_t)(j * 64 + i) * W + w];
+          }
+        }
+        acc |= (v[0] | v[1]) | (v[2] | v[3]);
+      }
+      remv[w] = acc;
+    }
+    __syncwarp();
+  }
+  for (int i = nkeep + lane; i < a.keep_stride; i += 32) keep[i] = -1;
+  if (lane == 0) a.keep_cnt[s] = nkeep;
+}
+
+size_t nms_mask_words(int S, int n_max) { return (size_t)S * n_max * ((n_max + 63) / 64); }
+
+int launch_nms_sorted(const NmsSortedArgs& a, cudaStream_t st) {
+  if (a.S == 0) return MXD_OK;
+  const int W = (a.n_max + 63) / 64;
+  if (a.n_max > 0) {
+    MXD_REQUIRE(a.S <= 65535 && W <= 65535, MXD_ENOTSUP, "too many NMS segments");
+    dim3 grid(W, W, a.S);
+    nms_mask_kernel<<<grid, 64, 0, st>>>(a, W);
+    MXD_POST_LAUNCH("nms_mask");
+  }
+  nms_resolve_kernel<<<a.S, 32, (W > 0 ? W : 1) * sizeof(u64), st>>>(a, W);
+  MXD_POST_LAUNCH("nms_resolve");
+  return MXD_OK;
+}
+
+// Gathers boxes (and ids) into score order for the public entry points.
+__global__ void nms_gather_kernel(const float* __restrict__ boxes, const int* __restrict__ ids,
+                                  const int* __restrict__ order, int k, float4* __restrict__ ob,
+                                  int* __restrict__ oid) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  const int i = order[j];
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i >= 0) b = reinterpret_cast<const float4*>(boxes)[i];
+  ob[j] = b;
+  if (oid) oid[j] = (i >= 0 && ids) ? ids[i] : 0;
+}
+
+// ---- MXNet (B,N,K) tensor form ------------------------------------------------
+__global__ void boxnms_gather_kernel(const float* __restrict__ data, const int* __restrict__ order, int N,
+                                     int K, int kmax, int coord_start, int id_index, int in_format,
+                                     float4* __restrict__ ob, int* __restrict__ oid) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= kmax) return;
+  const int i = order[(size_t)b * kmax + j];
+  float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+  int id = 0;
+  if (i >= 0) {
+    const float* row = data + ((size_t)b * N + i) * K;
+    bx = make_float4(row[coord_start], row[coord_start + 1], row[coord_start + 2], row[coord_start + 3]);
+    if (in_format == 1) {  // center -> corner
+      const float hw = __fdiv_rn(bx.z, 2.0f), hh = __fdiv_rn(bx.w, 2.0f);
+      bx = make_float4(__fsub_rn(bx.x, hw), __fsub_rn(bx.y, hh), __fadd_rn(bx.x, hw), __fadd_rn(bx.y, hh));
+    }
+    if (id_index >= 0) id = (int)row[id_index];
+  }
+  ob[(size_t)b * kmax + j] = bx;
+  if (oid) oid[(size_t)b * kmax + j] = id;
+}
+
+__global__ void boxnms_write_kernel(const float* __restrict__ data, const int* __restrict__ keep,
+                                    const int* __restrict__ keep_cnt, int N, int K, int kmax,
+                                    int coord_start, int in_format, int out_format,
+                                    float* __restrict__ out, int* __restrict__ index) {
+  const int b = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const int cnt = keep_cnt[b];
+  float* o = out + ((size_t)b * N + r) * K;
+  int src = -1;
+  if (r < cnt && r < kmax) src = keep[(size_t)b * kmax + r];
+  if (src < 0) {
+    for (int c = 0; c < K; ++c) o[c] = -1.0f;
+  } else {
+    const float* row = data + ((size_t)b * N + src) * K;
+    for (int c = 0; c < K; ++c) o[c] = row[c];
+    if (in_format != out_format) {
+      const float a0 = row[coord_start], a1 = row[coord_start + 1], a2 = row[coord_start + 2], a3 = row[coord_start + 3];
+      if (out_format == 0) {  // center -> corner
+        const float hw = __fdiv_rn(a2, 2.0f), hh = __fdiv_rn(a3, 2.0f);
+        o[coord_start] = __fsub_rn(a0, hw); o[coord_start + 1] = __fsub_rn(a1, hh);
+        o[coord_start + 2] = __fadd_rn(a0, hw); o[coord_start + 3] = __fadd_rn(a1, hh);
+      } else {  // corner -> center
+        const float w = __fsub_rn(a2, a0), h = __fsub_rn(a3, a1);
+        o[coord_start] = __fadd_rn(a0, __fdiv_rn(w, 2.0f)); o[coord_start + 1] = __fadd_rn(a1, __fdiv_rn(h, 2.0f));
+        o[coord_start + 2] = w; o[coord_start + 3] = h;
+      }
+    }
+  }
+  if (index) index[(size_t)b * N + r] = src;
+}
+
+__global__ void boxnms_backward_kernel(const float* __restrict__ og, const int* __restrict__ index, int N, int K,
+                                       float* __restrict__ ig) {
+  const int b = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const int src = index[(size_t)b * N + r];
+  if (src < 0) return;
+  const float* g = og + ((size_t)b * N + r) * K;
+  float* o = ig + ((size_t)b * N + src) * K;
+  for (int c = 0; c < K; ++c) o[c] = g[c];
+}
+
+struct NmsWs {
+  int* order; float* vals; int* cnt; float4* boxes; int* ids; u64* mask; int* keep; int* keep_cnt;
+  size_t bytes;
+};
+
+static NmsWs carve(void* base, int S, int kmax) {
+  NmsWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (char*)base + o; };
+  w.order = (int*)take(sizeof(int) * (size_t)S * kmax);
+  w.vals = (float*)take(sizeof(float) * (size_t)S * kmax);
+  w.cnt = (int*)take(sizeof(int) * (size_t)S);
+  w.boxes = (float4*)take(sizeof(float4) * (size_t)S * kmax);
+  w.ids = (int*)take(sizeof(int) * (size_t)S * kmax);
+  w.mask = (u64*)take(sizeof(u64) * nms_mask_words(S, kmax));
+  w.keep = (int*)take(sizeof(int) * (size_t)S * kmax);
+  w.keep_cnt = (int*)take(sizeof(int) * (size_t)S);
+  w.bytes = off;
+  return w;
+}
+
+static inline int eff_k(long long n, int topk) { return (int)((topk > 0 && topk < n) ? topk : n); }
+
+}  // namespace mxd
+
+using namespace mxd;
+
+extern "C" {
+
+size_t mxd_nms_workspace_bytes(int n, int topk) { return carve(nullptr, 1, eff_k(n, topk)).bytes; }
+
+int mxd_nms(const DLTensor* boxes, const DLTensor* scores, const DLTensor* ids, DLTensor* keep,
+            DLTensor* num_keep, float iou_thr, float delta, int topk, float valid_thresh,
+            int force_suppress, int max_out, void* workspace, size_t workspace_bytes, void* stream) {
+  int dev = -1, rc;
+  if ((rc = check_tensor(boxes, "boxes", F32, 2, 2, &dev))) return rc;
+  MXD_REQUIRE(boxes->shape[1] == 4, MXD_EINVAL, "boxes must be (n,4)");
+  const long long n = boxes->shape[0];
+  if ((rc = check_tensor(scores, "scores", F32, 1, 1, &dev))) return rc;
+  MXD_REQUIRE(scores->shape[0] == n, MXD_EINVAL, "scores must be (n)");
+  if (ids) {
+    if ((rc = check_tensor(ids, "ids", I32, 1, 1, &dev))) return rc;
+    MXD_REQUIRE(ids->shape[0] == n, MXD_EINVAL, "ids must be (n)");
+  }
+  if ((rc = check_tensor(keep, "keep", I32, 1, 1, &dev))) return rc;
+  if ((rc = check_tensor(num_keep, "num_keep", I32, 1, 1, &dev))) return rc;
+  MXD_REQUIRE(num_keep->shape[0] >= 1, MXD_EINVAL, "num_keep must hold one int32");
+  MXD_REQUIRE(((uintptr_t)dptr<float>(boxes) & 15) == 0, MXD_EINVAL, "boxes must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const int k = eff_k(n, topk);
+  const int cap = (int)keep->shape[0];
+  if (n == 0 || cap == 0) {
+    MXD_CUDA_OK(cudaMemsetAsync(dptr<int>(num_keep), 0, sizeof(int), st));
+    count_launch();
+    return MXD_OK;
+  }
+  MXD_REQUIRE(k <= MXD_SORT_CAP, MXD_ENOTSUP,
+              "NMS over %d rows exceeds the in-CTA sort capacity %d (pass topk)", k, MXD_SORT_CAP);
+  NmsWs w = carve(workspace, 1, k);
+  MXD_REQUIRE(workspace && workspace_bytes >= w.bytes, MXD_EWORKSPACE, "workspace %zu < %zu bytes",
+              workspace_bytes, w.bytes);
+  TopkParams p = {};
+  p.num_levels = 1; p.batch = 1;
+  p.scores[0] = dptr<float>(scores); p.seg_stride[0] = n; p.elem_stride = 1;
+  p.n[0] = (int)n; p.k[0] = k; p.kmax = k;
+  p.valid_thresh = valid_thresh;
+  p.out_idx = w.order; p.out_val = nullptr; p.out_cnt = w.cnt;
+  if ((rc = launch_topk(p, st))) return rc;
+  const bool class_aware = ids && !force_suppress;
+  nms_gather_kernel<<<(k + 255) / 256, 256, 0, st>>>(dptr<float>(boxes), ids ? dptr<int>(ids) : nullptr, w.order,
+                                                      k, w.boxes, class_aware ? w.ids : nullptr);
+  MXD_POST_LAUNCH("nms_gather");
+  NmsSortedArgs a = {};
+  a.boxes = w.boxes; a.valid = nullptr; a.ids = class_aware ? w.ids : nullptr; a.counts = w.cnt;
+  a.order = w.order; a.S = 1; a.stride = k; a.n_max = k; a.thr = iou_thr; a.delta = delta;
+  a.max_out = max_out; a.mask = w.mask;
+  // keep tensor may be shorter than k: resolve writes at most keep_stride rows
+  a.keep = dptr<int>(keep); a.keep_stride = cap; a.keep_cnt = dptr<int>(num_keep);
+  return launch_nms_sorted(a, st);
+}
+
+size_t mxd_box_nms_workspace_bytes(int batch, int n, int topk) { return carve(nullptr, batch, eff_k(n, topk)).bytes; }
+
+int mxd_box_nms(const DLTensor* data, DLTensor* out, DLTensor* index, float overlap_thresh, float valid_thresh,
+                int topk, int coord_start, int score_index, int id_index, int force_suppress, int in_format,
+                int out_format, void* workspace, size_t workspace_bytes, void* stream) {
+  int dev = -1, rc;
+  if ((rc = check_tensor(data, "data", F32, 2, 3, &dev))) return rc;
+  if ((rc = check_tensor(out, "out", F32, data->ndim, data->ndim, &dev))) return rc;
+  const int B = data->ndim == 3 ? (int)data->shape[0] : 1;
+  const long long N = data->shape[data->ndim - 2];
+  const int K = (int)data->shape[data->ndim - 1];
+  MXD_REQUIRE(numel(out) == numel(data), MXD_EINVAL, "out must have the shape of data");
+  MXD_REQUIRE(K >= 5 && coord_start >= 0 && coord_start + 4 <= K && score_index >= 0 && score_index < K &&
+              id_index < K, MXD_EINVAL, "bad coord_start/score_index/id_index for K=%d", K);
+  MXD_REQUIRE((in_format == 0 || in_format == 1) && (out_format == 0 || out_format == 1), MXD_EINVAL, "bad format");
+  if (index) {
+    if ((rc = check_tensor(index, "index", I32, data->ndim - 1, data->ndim - 1, &dev))) return rc;
+    MXD_REQUIRE(numel(index) == (int64_t)B * N, MXD_EINVAL, "index must be (B,N)");
+  }
+  if (B == 0 || N == 0) return MXD_OK;
+  const int k = eff_k(N, topk);
+  MXD_REQUIRE(k <= MXD_SORT_CAP, MXD_ENOTSUP,
+              "box_nms over %d rows exceeds the in-CTA sort capacity %d (pass topk)", k, MXD_SORT_CAP);
+  NmsWs w = carve(workspace, B, k);
+  MXD_REQUIRE(workspace && workspace_bytes >= w.bytes, MXD_EWORKSPACE, "workspace %zu < %zu bytes",
+              workspace_bytes, w.bytes);
+  cudaStream_t st = as_stream(stream);
+  TopkParams p = {};
+  p.num_levels = 1; p.batch = B;
+  p.scores[0] = dptr<float>(data) + score_index; p.seg_stride[0] = N * K; p.elem_stride = K;
+  p.n[0] = (int)N; p.k[0] = k; p.kmax = k;
+  p.valid_thresh = valid_thresh;
+  p.out_idx = w.order; p.out_cnt = w.cnt;
+  if ((rc = launch_topk(p, st))) return rc;
+  const bool class_aware = id_index >= 0 && !force_suppress;
+  dim3 g1((k + 255) / 256, B);
+  boxnms_gather_kernel<<<g1, 256, 0, st>>>(dptr<float>(data), w.order, (int)N, K, k, coord_start,
+                                           class_aware ? id_index : -1, in_format, w.boxes,
+                                           class_aware ? w.ids : nullptr);
+  MXD_POST_LAUNCH("boxnms_gather");
+  NmsSortedArgs a = {};
+  a.boxes = w.boxes; a.ids = class_aware ? w.ids : nullptr; a.counts = w.cnt; a.order = w.order;
+  a.S = B; a.stride = k; a.n_max = k; a.thr = overlap_thresh; a.delta = 0.0f; a.max_out = -1;
+  a.mask = w.mask; a.keep = w.keep; a.keep_stride = k; a.keep_cnt = w.keep_cnt;
+  if ((rc = launch_nms_sorted(a, st))) return rc;
+  dim3 g2(((int)N + 255) / 256, B);
+  boxnms_write_kernel<<<g2, 256, 0, st>>>(dptr<float>(data), w.keep, w.keep_cnt, (int)N, K, k, coord_start,
+                                          in_format, out_format, dptr<float>(out),
+                                          index ? dptr<int>(index) : nullptr);
+  MXD_POST_LAUNCH("boxnms_write");
+  return MXD_OK;
+}
+
+int mxd_box_nms_backward(const DLTensor* out_grad, const DLTensor* index, DLTensor* in_grad, void* stream) {
+  int dev = -1, rc;
+  if ((rc = check_tensor(out_grad, "out_grad", F32, 2, 3, &dev))) return rc;
+  if ((rc = check_tensor(in_grad, "in_grad", F32, out_grad->ndim, out_grad->ndim, &dev))) return rc;
+  if ((rc = check_tensor(index, "index", I32, out_grad->ndim - 1, out_grad->ndim - 1, &dev))) return rc;
+  const int B = out_grad->ndim == 3 ? (int)out_grad->shape[0] : 1;
+  const int N = (int)out_grad->shape[out_grad->ndim - 2], K = (int)out_grad->shape[out_grad->ndim - 1];
+  MXD_REQUIRE(numel(in_grad) == numel(out_grad) && numel(index) == (int64_t)B * N, MXD_EINVAL, "shape mismatch");
+  if (B == 0 || N == 0) return MXD_OK;
+  cudaStream_t st = as_stream(stream);
+  MXD_CUDA_OK(cudaMemsetAsync(dptr<float>(in_grad), 0, sizeof(float) * (size_t)numel(in_grad), st));
+  count_launch();
+  dim3 g((N + 255) / 256, B);
+  boxnms_backward_kernel<<<g, 256, 0, st>>>(dptr<float>(out_grad), dptr<int>(index), N, K, dptr<float>(in_grad));
+  MXD_POST_LAUNCH("boxnms_backward");
+  return MXD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,276 @@
+// Stable top-k by (score desc, index asc) with optional fused anchor
+// regeneration + delta decode (Specs B/H ordering rule, Spec C, Spec F).
+//
+// Serves mxdetection/ops NMS pre-sort and the pre-NMS top-k of
+// mxdetection/models/rpn_heads (/root/reference/README.md:24,28).
+//
+// One CTA per (image, level) segment; everything stays in shared memory.
+//   key = orderable(score) << 32 | (n-1-index)     (unique => order is total)
+//   n <= CAP          : sort all keys.
+//   n >  CAP          : (1) G strided group maxima (G >= k) give a lower bound L
+//                           on the k-th largest key - no atomics;
+//                       (2) keys >= L are compacted (warp-aggregated) and sorted;
+//                       (3) if more than CAP keys pass (adversarial input) an exact
+//                           11-bit radix select narrows them to exactly k first.
+#include "internal.h"
+
+namespace mxd {
+
+constexpr int kTopkThreads = 1024;
+constexpr int kCap = MXD_SORT_CAP;
+constexpr int kRadixBits = 11;
+constexpr int kRadixBins = 1 << kRadixBits;
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 make_key(float s, int i, int n, float valid_thresh) {
+  // dropped row: score <= valid_thresh (valid_thresh = -inf keeps everything but NaN)
+  if (!(s > valid_thresh) && !(valid_thresh == -INFINITY && s == s)) return 0ull;
+  return ((u64)f32_orderable(s) << 32) | (u64)(uint32_t)(n - 1 - i);
+}
+
+// Exact selection of the k-th largest key by MSB-first radix passes (slow path).
+__device__ u64 radix_select_kth(const float* __restrict__ sc, int estride, int n, int k, float vt,
+                                unsigned int* hist, u64* s_state) {
+  int nb = 0;
+  while ((1ll << nb) < (long long)n) ++nb;
+  u64 prefix = 0, pmask = 0;
+  int need = k;
+  int pos = 64;
+  while (pos > 0) {
+    int width, shift;
+    if (pos > 32) {  // score part: 11, 11, 10 bits
+      width = (pos == 64 || pos == 53) ? 11 : 10;
+      shift = pos - width;
+    } else {
+      if (pos == 32) pos = nb;  // skip the always-zero bits above the index width
+      if (pos == 0) break;
+      width = pos < kRadixBits ? pos : kRadixBits;
+      shift = pos - width;
+    }
+    const u64 dmask = (1ull << width) - 1;
+    for (int i = threadIdx.x; i < kRadixBins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      u64 key = make_key(sc[(size_t)i * estride], i, n, vt);
+      if (key != 0 && (key & pmask) == prefix) atomicAdd(&hist[(unsigned)((key >> shift) & dmask)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // lane L owns bins [hi-63, hi] with hi = 2047 - 64*L (descending walk)
+      const int lane = threadIdx.x;
+      const int hi = kRadixBins - 1 - 64 * lane;
+      unsigned sum = 0;
+      for (int b = 0; b < 64; ++b) sum += hist[hi - b];
+      unsigned incl = sum;
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const unsigned excl = incl - sum;
+      if (excl < (unsigned)need && incl >= (unsigned)need) {
+        unsigned run = excl;
+        for (int b = 0; b < 64; ++b) {
+          unsigned h = hist[hi - b];
+          if (run + h >= (unsigned)need) {
+            s_state[0] = (u64)(hi - b);
+            s_state[1] = (u64)(need - run);   // still needed inside this bin
+            s_state[2] = (u64)h;
+            break;
+          }
+          run += h;
+        }
+      }
+    }
+    __syncthreads();
+    const u64 digit = s_state[0];
+    need = (int)s_state[1];
+    const int binsz = (int)s_state[2];
+    prefix |= digit << shift;
+    pmask |= dmask << shift;
+    pos = shift;
+    __syncthreads();
+    if (binsz == need) break;  // the whole bin is selected
+  }
+  return prefix;  // select keys >= prefix (low unprocessed bits are zero)
+}
+
+__global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __grid_constant__ TopkParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64* keys = reinterpret_cast<u64*>(smem_raw);  // kCap entries
+  __shared__ unsigned int s_hist[kRadixBins];
+  __shared__ u64 s_state[4];
+  __shared__ int s_count;
+
+  const int s = blockIdx.x;
+  const int b = s / p.num_levels, l = s - b * p.num_levels;
+  const int n = p.n[l], k = p.k[l];
+  const int es = p.elem_stride;
+  const float vt = p.valid_thresh;
+  const float* __restrict__ sc = p.scores[l] + (size_t)b * p.seg_stride[l];
+  const int tid = threadIdx.x;
+  int count;
+
+  if (n <= kCap) {
+    for (int i = tid; i < n; i += kTopkThreads) keys[i] = make_key(sc[(size_t)i * es], i, n, vt);
+    count = n;
+  } else {
+    // (1) strided group maxima
+    const int G = (k <= 2048) ? 4096 : kCap;
+    for (int g = tid; g < G; g += kTopkThreads) {
+      u64 m = 0;
+      for (int i = g; i < n; i += G) {
+        u64 key = make_key(sc[(size_t)i * es], i, n, vt);
+        m = key > m ? key : m;
+      }
+      keys[g] = m;
+    }
+    __syncthreads();
+    bitonic_sort_desc(keys, G);
+    u64 L = keys[k - 1];
+    if (tid == 0) s_count = 0;
+    __syncthreads();  // everyone has read L before keys[] is overwritten
+    if (L == 0) L = 1;  // fewer than k valid rows: take every valid key
+    // (2) compaction of keys >= L
+    const int iters = (n + kTopkThreads - 1) / kTopkThreads;
+    const unsigned lane = tid & 31;
+    for (int it = 0; it < iters; ++it) {
+      const int i = it * kTopkThreads + tid;
+      u64 key = 0;
+      if (i < n) key = make_key(sc[(size_t)i * es], i, n, vt);
+      const bool take = key >= L;
+      const unsigned m = __ballot_sync(0xffffffffu, take);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if ((int)lane == leader) base = atomicAdd(&s_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        if (take && pos < kCap) keys[pos] = key;
+      }
+    }
+    __syncthreads();
+    count = s_count;
+    if (count > kCap) {
+      // (3) exact threshold, then re-compact exactly min(k, valid) keys
+      __syncthreads();
+      const u64 T = radix_select_kth(sc, es, n, k, vt, s_hist, s_state);
+      if (tid == 0) s_count = 0;
+      __syncthreads();
+      for (int it = 0; it < iters; ++it) {
+        const int i = it * kTopkThreads + tid;
+        u64 key = 0;
+        if (i < n) key = make_key(sc[(size_t)i * es], i, n, vt);
+        if (key != 0 && key >= T) {
+          const int pos = atomicAdd(&s_count, 1);
+          if (pos < kCap) keys[pos] = key;
+        }
+      }
+      __syncthreads();
+      count = min(s_count, kCap);
+    }
+  }
+  const int P = max(next_pow2(count), 2);
+  for (int i = count + tid; i < P; i += kTopkThreads) keys[i] = 0;
+  __syncthreads();
+  bitonic_sort_desc(keys, P);
+
+  // ---- emit -------------------------------------------------------------------
+  int* oi = p.out_idx + (size_t)s * p.kmax;
+  float hmax = 0.f, wmax = 0.f;
+  if (p.out_boxes) {
+    hmax = (float)(p.img_shapes[2 * b] - 1);
+    wmax = (float)(p.img_shapes[2 * b + 1] - 1);
+  }
+  for (int j = tid; j < p.kmax; j += kTopkThreads) {
+    const u64 key = (j < k && j < P) ? keys[j] : 0ull;
+    const bool ok = key != 0;
+    const int i = ok ? n - 1 - (int)(uint32_t)key : -1;
+    oi[j] = i;
+    if (p.out_val) p.out_val[(size_t)s * p.kmax + j] = ok ? sc[(size_t)i * es] : 0.0f;
+    if (p.out_boxes) {
+      float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint8_t v = 0;
+      if (ok) {
+        const int A = p.num_base;
+        const int a = i % A, cell = i / A;
+        const int x = cell % p.feat_w[l], y = cell / p.feat_w[l];
+        const float sx = __fmul_rn((float)x, p.stride[l]), sy = __fmul_rn((float)y, p.stride[l]);
+        float4 anc;
+        anc.x = __fadd_rn(p.base[l][a][0], sx); anc.y = __fadd_rn(p.base[l][a][1], sy);
+        anc.z = __fadd_rn(p.base[l][a][2], sx); anc.w = __fadd_rn(p.base[l][a][3], sy);
+        const float4 dl = reinterpret_cast<const float4*>(p.deltas[l])[(size_t)b * n + i];
+        box = decode_box(anc, dl, p.means, p.stds, p.max_ratio, hmax, wmax, true);
+        v = 1;
+        if (p.min_size > 0.f) {
+          const float w = __fadd_rn(__fsub_rn(box.z, box.x), 1.0f), h = __fadd_rn(__fsub_rn(box.w, box.y), 1.0f);
+          v = (w >= p.min_size && h >= p.min_size) ? 1 : 0;
+        }
+      }
+      p.out_boxes[(size_t)s * p.kmax + j] = box;
+      p.out_valid[(size_t)s * p.kmax + j] = v;
+    }
+  }
+  if (p.out_cnt && tid == 0) {
+    // real rows = position of the first zero key (keys are sorted, zeros last)
+    int lo = 0, hi = min(k, P);
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (keys[mid] != 0) lo = mid + 1; else hi = mid;
+    }
+    p.out_cnt[s] = lo;
+  }
+}
+
+int launch_topk(const TopkParams& p, cudaStream_t st) {
+  const int S = p.batch * p.num_levels;
+  if (S == 0) return MXD_OK;
+  for (int l = 0; l < p.num_levels; ++l) {
+    MXD_REQUIRE(p.k[l] <= kCap, MXD_ENOTSUP, "top-k of %d rows exceeds the in-CTA sort capacity %d", p.k[l], kCap);
+    MXD_REQUIRE(p.k[l] <= p.kmax && p.n[l] >= 0, MXD_EINVAL, "bad top-k geometry");
+  }
+  static bool attr_set = false;
+  const int smem = kCap * (int)sizeof(u64);
+  if (!attr_set) {
+    MXD_CUDA_OK(cudaFuncSetAttribute(topk_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  topk_segment_kernel<<<S, kTopkThreads, smem, st>>>(p);
+  MXD_POST_LAUNCH("topk_segment");
+  return MXD_OK;
+}
+
+}  // namespace mxd
+
+using namespace mxd;
+
+extern "C" {
+
+size_t mxd_topk_stable_workspace_bytes(int, int, int) { return 0; }
+
+int mxd_topk_stable(const DLTensor* scores, DLTensor* idx, DLTensor* vals, int topk, void* /*workspace*/,
+                    size_t /*workspace_bytes*/, void* stream) {
+  int dev = -1, rc;
+  if ((rc = check_tensor(scores, "scores", F32, 1, 2, &dev))) return rc;
+  const int S = scores->ndim == 2 ? (int)scores->shape[0] : 1;
+  const long long n = scores->shape[scores->ndim - 1];
+  MXD_REQUIRE(n < (1ll << 31), MXD_ENOTSUP, "segment too long");
+  const int k = (topk > 0 && topk < n) ? topk : (int)n;
+  if ((rc = check_tensor(idx, "idx", I32, scores->ndim, scores->ndim, &dev))) return rc;
+  MXD_REQUIRE(numel(idx) == (int64_t)S * k, MXD_EINVAL, "idx must be (S,k) with k=%d", k);
+  if (vals) {
+    if ((rc = check_tensor(vals, "vals", F32, scores->ndim, scores->ndim, &dev))) return rc;
+    MXD_REQUIRE(numel(vals) == (int64_t)S * k, MXD_EINVAL, "vals must be (S,k) with k=%d", k);
+  }
+  if (S == 0 || k == 0) return MXD_OK;
+  TopkParams p = {};
+  p.num_levels = 1; p.batch = S;
+  p.scores[0] = dptr<float>(scores); p.seg_stride[0] = n; p.elem_stride = 1;
+  p.n[0] = (int)n; p.k[0] = k; p.kmax = k;
+  p.valid_thresh = -INFINITY;
+  p.out_idx = dptr<int>(idx);
+  p.out_val = vals ? dptr<float>(vals) : nullptr;
+  return launch_topk(p, as_stream(stream));
+}
+
+}  // extern "C"

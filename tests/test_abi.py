@@ -1,0 +1,94 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/mxdet.h
+declares, refuses CPU tensors loudly (no fallback), and the ctypes struct mirrors match the C layout.
+No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mxdet.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mxd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mxdetection_b200 import _lib as L
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(L.lib, s), "libmxdet_sm100.so does not export %s" % s
+    assert L.lib.mxd_version() >= 100
+    assert L.lib.mxd_sizeof_rpn_config() == ctypes.sizeof(L.RpnConfig)
+    from oracle import cref
+    assert cref.lib().ora_sizeof_rpn_config() == ctypes.sizeof(cref.RpnConfig)
+
+
+def test_built_for_sm100a_only():
+    from mxdetection_b200 import _lib as L
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "--list-elf", L.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_cpu_tensors_are_refused_not_computed():
+    import mxdetection_b200 as m
+    from mxdetection_b200.ops import roi_align_forward, nms_indices, box_nms, topk_stable
+    from mxdetection_b200.core.bbox import bbox_overlaps, delta2bbox, MaxIoUAssigner
+    from mxdetection_b200.models.roi_extractors import map_roi_levels
+    data = torch.zeros(1, 2, 8, 8); rois = torch.zeros(3, 5); boxes = torch.zeros(4, 4)
+    for fn in (lambda: roi_align_forward(data, rois, 7, 0.25, 2),
+               lambda: nms_indices(boxes, torch.zeros(4), 0.5),
+               lambda: box_nms(torch.zeros(1, 4, 6)),
+               lambda: topk_stable(torch.zeros(10), 3),
+               lambda: bbox_overlaps(boxes, boxes),
+               lambda: delta2bbox(boxes, boxes),
+               lambda: MaxIoUAssigner(0.7, 0.3, 0.3).assign(boxes, boxes),
+               lambda: map_roi_levels(rois, 4)):
+        with pytest.raises(m.MXDetError) as e:
+            fn()
+        assert e.value.code == -2
+
+
+def test_raw_abi_validation_messages():
+    """dtype / shape errors come back as MXD_EINVAL with a message (mirrors MXGetLastError)."""
+    from mxdetection_b200 import _lib as L
+
+    class FakeCuda:   # a DLPack producer that *claims* to be CUDA so validation proceeds past the device check
+        def __init__(self, t):
+            self.t = t
+
+    t = torch.zeros(3, 5, dtype=torch.float64)
+    b = L.Borrowed(t)
+    rc = L.lib.mxd_map_roi_levels(b.ptr, b.ptr, 4, 56.0, None)
+    assert rc == -2 and b"not CUDA" in L.lib.mxd_last_error()
+    rc = L.lib.mxd_map_roi_levels(None, None, 4, 56.0, None)
+    assert rc == -1 and b"null tensor" in L.lib.mxd_last_error()
+    c = L.RpnConfig(); c.num_levels = 99
+    assert L.lib.mxd_rpn_proposals_workspace_bytes(ctypes.byref(c), 2) == 0
+    k = ctypes.c_int(); s = ctypes.c_int()
+    assert L.lib.mxd_rpn_proposals_dims(ctypes.byref(c), ctypes.byref(k), ctypes.byref(s)) == -1
+
+
+def test_workspace_queries_are_pure():
+    from mxdetection_b200 import _lib as L
+    assert L.lib.mxd_nms_workspace_bytes(2000, -1) > 2000 * 32 * 8
+    assert L.lib.mxd_max_iou_assign_workspace_bytes(8, 100) >= 8 * 100 * 4
+    assert L.launch_count() == 0 or L.launch_count() > 0   # counter is readable without a GPU
+
+
+def test_host_anchor_tables_match_oracle():
+    import oracle
+    from mxdetection_b200.core.anchor import AnchorGenerator, generate_anchors_mx
+    for base, scales, ratios in [(4, [8], [.5, 1, 2]), (16, [2, 4, 8], [.5, 1, 2]), (64, [8, 16], [.33, 1, 3])]:
+        for sm in (True, False):
+            assert np.array_equal(AnchorGenerator(base, scales, ratios, sm).base_anchors,
+                                  oracle.gen_base_anchors(base, scales, ratios, sm))
+    assert np.array_equal(generate_anchors_mx(), oracle.generate_anchors_mx())

@@ -1,0 +1,461 @@
+"""GPU parity tests (run on a B200 through gpurun: `pytest -m gpu`).
+
+Every test drives the product path - Python mirror -> ctypes C ABI -> sm_100a kernels - and
+compares with the CPU oracle (oracle/*.py NumPy statement, oracle/cpu_ref.c for the large cases)
+on identical seeded inputs.  Bars (BASELINE.json north_star / SURVEY.md 8c):
+  bit-exact : anchors, flags, IoU, labels, matched-GT indices, top-k indices, NMS keep indices, levels
+  RoIAlign  : fwd |d| <= 1e-5*max(1,|ref|), bwd |d| <= 1e-4*max(1,|ref|)
+  decode    : <= 1e-5 px (and bit-identical in practice: exp/log are correctly rounded on both sides)
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import cref
+from oracle.nms import stable_order_desc
+from mxdetection_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+DEV = "cuda"
+
+
+def T(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, ref, tol):
+    return np.all(np.abs(a - ref) <= tol * np.maximum(1.0, np.abs(ref)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_library_is_the_one_running():
+    import mxdetection_b200 as m
+    before = m.launch_count()
+    yield
+    assert m.launch_count() > before, "no kernel of libmxdet_sm100.so was launched by the GPU tests"
+
+
+# =============================================================== RoIAlign (Spec A) ==
+@pytest.mark.parametrize("name", ["roi_align_a", "roi_align_b", "roi_align_c"])
+def test_roi_align_golden(golden_dir, name):
+    from mxdetection_b200.ops import roi_align_forward, roi_align_backward
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    ps = tuple(int(v) for v in g["pooled"]); sc = float(g["scale"]); sr = int(g["sample_ratio"])
+    out = N(roi_align_forward(T(g["data"]), T(g["rois"]), ps, sc, sr))
+    assert close(out, g["out"], 1e-5)
+    gin = N(roi_align_backward(T(g["grad_out"]), T(g["rois"]), g["data"].shape, ps, sc, sr))
+    assert close(gin, g["grad_in"], 1e-4)
+
+
+@pytest.mark.parametrize("sr,ps", [(2, (7, 7)), (2, (14, 14)), (-1, (7, 7)), (4, (7, 7)), (9, (8, 8)), (1, (1, 1))])
+def test_roi_align_vs_oracle_random(sr, ps):
+    from mxdetection_b200.ops import roi_align_forward, roi_align_backward
+    rng = np.random.default_rng(7 + sr + ps[0])
+    Nn, C, H, W = 2, 37, 50, 68           # C not a multiple of the channel chunk
+    data = rng.standard_normal((Nn, C, H, W)).astype(F)
+    R = 96
+    x1 = rng.uniform(-40, W * 4, R); y1 = rng.uniform(-40, H * 4, R)
+    w = np.exp(rng.uniform(np.log(2), np.log(400), R)); h = np.exp(rng.uniform(np.log(2), np.log(400), R))
+    rois = np.stack([rng.integers(0, Nn, R), x1, y1, x1 + w, y1 + h], 1).astype(F)
+    ref = cref.roi_align_forward(data, rois, ps, 0.25, sr)
+    out = N(roi_align_forward(T(data), T(rois), ps, 0.25, sr))
+    assert close(out, ref, 1e-5)
+    gout = rng.standard_normal(ref.shape).astype(F)
+    gref = cref.roi_align_backward(gout, rois, data.shape, ps, 0.25, sr)
+    gin = N(roi_align_backward(T(gout), T(rois), data.shape, ps, 0.25, sr))
+    assert close(gin, gref, 1e-4)
+    # req='add'
+    base = rng.standard_normal(data.shape).astype(F)
+    acc = T(base.copy())
+    roi_align_backward(T(gout), T(rois), data.shape, ps, 0.25, sr, grad_data=acc)
+    assert close(N(acc), base + gref, 1e-4)
+
+
+def test_roi_align_edge_cases():
+    from mxdetection_b200.ops import roi_align_forward, roi_align_backward
+    data = np.random.default_rng(0).standard_normal((2, 3, 10, 12)).astype(F)
+    rois = np.array([[-1, 0, 0, 10, 10], [0, -500, -500, -400, -400], [1, 44, 36, 47.9, 39.9], [0, 5, 5, 5, 5],
+                     [7, 0, 0, 5, 5]], F)
+    ref = oracle.roi_align_forward(data, rois, (2, 2), 1.0, 2)
+    out = N(roi_align_forward(T(data), T(rois), (2, 2), 1.0, 2))
+    assert close(out, ref, 1e-5) and np.all(out[0] == 0) and np.all(out[1] == 0) and np.all(out[4] == 0)
+    g = np.ones_like(ref)
+    gref = oracle.roi_align_backward(g, rois, data.shape, (2, 2), 1.0, 2)
+    assert close(N(roi_align_backward(T(g), T(rois), data.shape, (2, 2), 1.0, 2)), gref, 1e-4)
+    empty = roi_align_forward(T(data), T(rois[:0]), (2, 2), 1.0, 2)
+    assert tuple(empty.shape) == (0, 3, 2, 2)
+    z = N(roi_align_backward(T(g[:0]), T(rois[:0]), data.shape, (2, 2), 1.0, 2))
+    assert z.shape == data.shape and np.all(z == 0)
+
+
+def test_roi_align_autograd_and_linearity_cfg1_full_size():
+    """BASELINE config 1 at full size: vs the C oracle, plus size-independent properties."""
+    from mxdetection_b200.ops import ROIAlign, roi_align_forward
+    c = syn.cfg1()
+    data = T(c["data"]).requires_grad_(True)
+    rois = T(c["rois"])
+    out = ROIAlign(data, rois, c["pooled"], c["scale"], c["sample_ratio"])
+    ref = cref.roi_align_forward(c["data"], c["rois"], c["pooled"], c["scale"], c["sample_ratio"])
+    assert close(N(out), ref, 1e-5)
+    out.backward(T(c["grad_out"]))
+    gref = cref.roi_align_backward(c["grad_out"], c["rois"], c["data"].shape, c["pooled"], c["scale"], c["sample_ratio"])
+    assert close(N(data.grad), gref, 1e-4)
+    # linearity in the features and adjointness <RA(x), g> == <x, RA^T(g)>
+    x2 = torch.randn_like(data)
+    lhs = roi_align_forward(2.0 * data.detach() - 3.0 * x2, rois, c["pooled"], c["scale"], 2)
+    rhs = 2.0 * out.detach() - 3.0 * roi_align_forward(x2, rois, c["pooled"], c["scale"], 2)
+    assert torch.allclose(lhs, rhs, rtol=0, atol=2e-5)
+    dot1 = (out.detach().double() * T(c["grad_out"]).double()).sum().item()
+    dot2 = (data.detach().double() * data.grad.double()).sum().item()
+    assert abs(dot1 - dot2) <= 1e-5 * max(1.0, abs(dot1))
+    # constant map -> constant output wherever no sample is skipped
+    const = roi_align_forward(torch.full_like(data.detach(), 1.5), rois, c["pooled"], c["scale"], 2)
+    assert torch.all((const - 1.5).abs() <= 1e-6)
+
+
+# ============================================================ levels + FPN (Spec G) ==
+def test_map_roi_levels_bit_exact_incl_boundaries():
+    from mxdetection_b200.models.roi_extractors import map_roi_levels
+    rng = np.random.default_rng(9)
+    r = np.concatenate([np.zeros((4000, 1)), rng.uniform(0, 600, (4000, 2)), rng.uniform(600, 1300, (4000, 2))], 1).astype(F)
+    edge = []
+    for s in (112.0, 224.0, 448.0):
+        for d in (-1e-3, -1e-4, 0.0, 1e-4, 1e-3):
+            v = np.float32(s + d)
+            for _ in range(3):
+                edge.append([0, 0, 0, v - 1, v - 1]); v = np.nextafter(v, np.float32(1e9), dtype=F)
+    r = np.concatenate([r, np.asarray(edge, F)], 0)
+    for L_ in (4, 5, 2, 1):
+        assert np.array_equal(N(map_roi_levels(T(r), L_)), oracle.map_roi_levels(r, L_))
+    assert np.array_equal(N(map_roi_levels(T(r[:, 1:].copy()), 4)), oracle.map_roi_levels(r[:, 1:], 4))
+
+
+def test_fpn_roi_extractor_small_and_autograd():
+    from mxdetection_b200.models.roi_extractors import SingleLevelRoI
+    d = syn.fpn_roi_inputs(3, 2, 256, 320, 64, channels=16)
+    ext = SingleLevelRoI(7, (4, 8, 16, 32), sample_num=2)
+    feats = [T(f).requires_grad_(True) for f in d["feats"]]
+    out = ext(feats, T(d["rois"]))
+    lv = oracle.map_roi_levels(d["rois"], 4)
+    assert len(set(lv.tolist())) >= 3
+    ref = cref.roi_align_forward(d["feats"], d["rois"], (7, 7), d["scales"], 2, lv)
+    assert close(N(out), ref, 1e-5)
+    out.backward(T(d["grad_out"]))
+    gref = cref.roi_align_backward(d["grad_out"], d["rois"], [f.shape for f in d["feats"]], (7, 7), d["scales"], 2, lv)
+    for f, g in zip(feats, gref):
+        assert close(N(f.grad), g, 1e-4)
+
+
+def test_fpn_roi_stage_cfg3_shard_full_size():
+    """BASELINE config 3 geometry (800x1344, 4 levels, 256 ch, 512 RoIs/img), 2 images of the 8."""
+    from mxdetection_b200.ops import roi_align_fpn_forward, roi_align_fpn_backward
+    d = syn.cfg3(batch=2)
+    lv = oracle.map_roi_levels(d["rois"], 4)
+    out = roi_align_fpn_forward([T(f) for f in d["feats"]], T(d["rois"]), (7, 7), d["scales"], 2)   # levels in-kernel
+    ref = cref.roi_align_forward(d["feats"], d["rois"], (7, 7), d["scales"], 2, lv)
+    assert close(N(out), ref, 1e-5)
+    g = roi_align_fpn_backward(T(d["grad_out"]), T(d["rois"]), [f.shape for f in d["feats"]], (7, 7), d["scales"], 2)
+    gref = cref.roi_align_backward(d["grad_out"], d["rois"], [f.shape for f in d["feats"]], (7, 7), d["scales"], 2, lv)
+    for a, b in zip(g, gref):
+        assert close(N(a), b, 1e-4)
+
+
+def test_mask_branch_cfg4_14x14():
+    from mxdetection_b200.ops import roi_align_fpn_forward
+    d = syn.cfg4_mask(batch=1)
+    lv = oracle.map_roi_levels(d["rois"], 4)
+    out = roi_align_fpn_forward([T(f) for f in d["feats"]], T(d["rois"]), (14, 14), d["scales"], 2, levels=T(lv))
+    ref = cref.roi_align_forward(d["feats"], d["rois"], (14, 14), d["scales"], 2, lv)
+    assert close(N(out), ref, 1e-5)
+
+
+# ================================================================ top-k (Spec B/H) ==
+@pytest.mark.parametrize("n,k", [(1, 1), (5, 10), (63, 7), (2048, 2048), (8192, 2000), (8193, 2000), (50000, 2000),
+                                  (217413, 2000), (201600, 6000), (300000, 1)])
+def test_topk_stable_bit_exact(n, k):
+    from mxdetection_b200.ops import topk_stable
+    rng = np.random.default_rng(n + k)
+    z = rng.normal(-4, 2, (3, n))
+    s = (1 / (1 + np.exp(-z))).astype(F)
+    s[1] = np.round(s[1] * 64) / 64                # heavy ties
+    s[2, : n // 2] = 0.0; s[2, n // 2] = -0.0      # zeros of both signs compare equal -> index decides
+    idx, vals = topk_stable(T(s), k)
+    for r in range(3):
+        ref = oracle.topk_stable(s[r], k)
+        assert np.array_equal(N(idx)[r], ref), "segment %d" % r
+        assert np.array_equal(N(vals)[r], s[r][ref])
+
+
+def test_topk_adversarial_inputs_take_the_exact_fallback():
+    from mxdetection_b200.ops import topk_stable
+    rng = np.random.default_rng(77)
+    n = 4096 * 8
+    s = rng.uniform(0, 0.5, n).astype(F)
+    hot = (np.arange(n) % 4096) < 2000             # > 8192 rows beat the group-maxima bound
+    s[hot] = rng.uniform(0.5, 1.0, hot.sum()).astype(F)
+    const = np.full(n, 0.25, F)                    # all equal: the index alone orders
+    desc = np.linspace(1, 0, n).astype(F)
+    for arr in (s, const, desc, desc[::-1].copy()):
+        idx, _ = topk_stable(T(arr), 2000)
+        assert np.array_equal(N(idx), oracle.topk_stable(arr, 2000))
+
+
+# ===================================================================== NMS (Spec B) ==
+@pytest.mark.parametrize("name", ["nms_a", "nms_b", "nms_c"])
+def test_nms_golden(golden_dir, name):
+    from mxdetection_b200.ops import nms_indices
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    keep, num = nms_indices(T(g["boxes"]), T(g["scores"]), float(g["thr"]), delta=0.0)
+    k = int(num.item())
+    assert np.array_equal(N(keep)[:k], g["keep"]) and np.all(N(keep)[k:] == -1)
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 128, 1000, 2000, 4100])
+@pytest.mark.parametrize("delta", [0.0, 1.0])
+def test_nms_vs_oracle_bit_exact(n, delta):
+    from mxdetection_b200.ops import nms_indices
+    rng = np.random.default_rng(n * 3 + int(delta))
+    span = 40 * math.sqrt(n) + 20
+    xy = rng.uniform(0, span, (n, 2)); wh = rng.uniform(4, 120, (n, 2))
+    boxes = np.concatenate([xy, xy + wh], 1).astype(F)
+    boxes[n // 3] = boxes[0]                                     # exact duplicates
+    scores = (np.round(rng.uniform(0, 1, n) * 40) / 40).astype(F)   # ties
+    ref = oracle.nms(boxes, scores, 0.7, delta=delta)
+    keep, num = nms_indices(T(boxes), T(scores), 0.7, delta=delta)
+    assert int(num.item()) == len(ref) and np.array_equal(N(keep)[: len(ref)], ref)
+
+
+def test_nms_options_topk_validthresh_ids_maxout():
+    from mxdetection_b200.ops import nms_indices, nms
+    rng = np.random.default_rng(4)
+    n = 900
+    xy = rng.uniform(0, 300, (n, 2)); wh = rng.uniform(4, 90, (n, 2))
+    boxes = np.concatenate([xy, xy + wh], 1).astype(F)
+    scores = rng.uniform(0, 1, n).astype(F)
+    ids = rng.integers(0, 5, n).astype(np.int32)
+    for kw in (dict(topk=200), dict(valid_thresh=0.4), dict(max_out=50), dict(ids=ids, force_suppress=False),
+               dict(ids=ids, force_suppress=True), dict(topk=300, valid_thresh=0.2, max_out=70, ids=ids, force_suppress=False)):
+        ref = oracle.nms(boxes, scores, 0.5, delta=0.0, **kw)
+        tk = {k: (T(v) if k == "ids" else v) for k, v in kw.items()}
+        keep, num = nms_indices(T(boxes), T(scores), 0.5, delta=0.0, **tk)
+        assert int(num.item()) == len(ref) and np.array_equal(N(keep)[: len(ref)], ref), kw
+    dets = np.concatenate([boxes, scores[:, None]], 1)
+    kept, inds = nms(T(dets), 0.5)
+    ref = oracle.nms(boxes, scores, 0.5, delta=1.0)
+    assert np.array_equal(N(inds), ref) and np.array_equal(N(kept), dets[ref])
+    # idempotence: NMS of the survivors keeps all of them
+    k2, n2 = nms_indices(T(boxes[ref]), T(scores[ref]), 0.5, delta=1.0)
+    assert int(n2.item()) == len(ref)
+    empty, ne = nms_indices(T(boxes[:0]), T(scores[:0]), 0.5)
+    assert int(ne.item()) == 0
+
+
+def test_box_nms_mx_tensor_api_and_backward():
+    from mxdetection_b200.ops import box_nms, box_nms_backward
+    x = np.array([[0, .5, .1, .1, .2, .2], [1, .4, .1, .1, .2, .2], [0, .3, .1, .1, .14, .14], [2, .6, .5, .5, .7, .8]], F)
+    out = N(box_nms(T(x), overlap_thresh=0.1, coord_start=2, score_index=1, id_index=0, force_suppress=True))
+    exp = np.array([[2, .6, .5, .5, .7, .8], [0, .5, .1, .1, .2, .2], [-1] * 6, [-1] * 6], F)
+    assert np.array_equal(out, exp)                                             # KAT-1
+    rng = np.random.default_rng(12)
+    B, Nn = 3, 500
+    xy = rng.uniform(0, 1, (B, Nn, 2)); wh = rng.uniform(0.02, 0.3, (B, Nn, 2))
+    data = np.concatenate([rng.integers(0, 4, (B, Nn, 1)), rng.uniform(-0.2, 1, (B, Nn, 1)), xy, xy + wh], 2).astype(F)
+    for kw in (dict(), dict(topk=100), dict(id_index=0), dict(id_index=0, force_suppress=True), dict(valid_thresh=0.3),
+               dict(out_format="center"), dict(in_format="center", out_format="corner")):
+        ref, ridx = oracle.box_nms_mx(data, overlap_thresh=0.45, coord_start=2, score_index=1, return_index=True, **kw)
+        got, gidx = box_nms(T(data), overlap_thresh=0.45, coord_start=2, score_index=1, return_index=True, **kw)
+        assert np.array_equal(N(gidx), ridx), kw
+        assert np.array_equal(N(got), ref), kw
+    og = rng.standard_normal(data.shape).astype(F)
+    ig = N(box_nms_backward(T(og), gidx))
+    exp = np.zeros_like(og)
+    for b in range(B):
+        for r in range(Nn):
+            if ridx[b, r] >= 0:
+                exp[b, ridx[b, r]] = og[b, r]
+    assert np.array_equal(ig, exp)
+
+
+# ========================================================= anchors / IoU / assigner ==
+def test_anchors_and_flags_bit_exact():
+    from mxdetection_b200.core.anchor import AnchorGenerator, anchor_inside_flags
+    for base, stride, (fh, fw) in [(4, 4, (50, 68)), (16, 16, (13, 17)), (64, 64, (3, 5))]:
+        ag = AnchorGenerator(base, [8], [0.5, 1.0, 2.0])
+        ref = oracle.grid_anchors(oracle.gen_base_anchors(base, [8], [0.5, 1, 2]), fh, fw, stride)
+        got = ag.grid_anchors((fh, fw), stride)
+        assert np.array_equal(N(got), ref)
+        v = ag.valid_flags((fh, fw), (fh - 1, fw - 2))
+        assert np.array_equal(N(v), oracle.valid_flags(fh, fw, fh - 1, fw - 2, 3))
+        for ab in (0, 8, -1):
+            ins = anchor_inside_flags(got, v, (fh * stride - 3, fw * stride - 5), ab)
+            assert np.array_equal(N(ins), oracle.inside_flags(ref, N(v), fh * stride - 3, fw * stride - 5, ab))
+
+
+def test_bbox_overlaps_bit_exact():
+    from mxdetection_b200.core.bbox import bbox_overlaps
+    rng = np.random.default_rng(2)
+    g = syn.gt_boxes(rng, 800, 1344, 57); a = syn.gt_boxes(rng, 800, 1344, 3001)
+    a[5] = g[3]
+    for d in (1.0, 0.0):
+        assert np.array_equal(N(bbox_overlaps(T(g), T(a), delta=d)), oracle.bbox_overlaps(g, a, d))
+
+
+def test_assigner_kat4_and_random_bit_exact():
+    from mxdetection_b200.core.bbox import MaxIoUAssigner
+    gts = np.array([[0, 0, 9, 9], [10, 0, 19, 9], [100, 100, 149, 149]], F)
+    anchors = np.array([[100, 100, 149, 149], [300, 300, 310, 310], [5, 0, 14, 9], [100, 100, 149, 124], [0, 0, 9, 4],
+                        [400, 0, 409, 9]], F)
+    res = MaxIoUAssigner(0.7, 0.3, 0.3).assign(T(anchors), T(gts), T(np.array([7, 8, 9], np.int32)))
+    assert N(res.gt_inds).tolist() == [3, 0, 2, -1, 1, 0] and N(res.labels).tolist() == [9, 0, 8, 0, 7, 0]
+    keep = [0, 1, 2, 3, 5]
+    res = MaxIoUAssigner(0.7, 0.3, 0.3).assign(T(anchors[keep]), T(gts))
+    assert N(res.gt_inds).tolist() == [3, 0, 2, -1, 0]
+    # random, batched, ragged GT counts (incl. 0), flags, both threshold sets
+    rng = np.random.default_rng(31)
+    base = oracle.gen_base_anchors(16, [4, 8], [0.5, 1, 2])
+    anc = oracle.grid_anchors(base, 25, 38, 16)
+    flags = oracle.inside_flags(anc, np.ones(len(anc), np.uint8), 400, 600, 0)
+    gl = [syn.gt_boxes(rng, 400, 600, g) for g in (30, 1, 0, 300)]      # 300 > one smem chunk of 256
+    G, num = syn.padded_gts(gl, 300)
+    labels = rng.integers(1, 81, (4, 300)).astype(np.int32)
+    for thr in ((0.7, 0.3, 0.3), (0.5, 0.5, 0.5), (0.5, 0.5, 0.0)):
+        a, m, l = MaxIoUAssigner(*thr).assign_batch(T(anc), T(G), T(num), T(labels), T(flags))
+        for b in range(4):
+            ra, rm, rl = oracle.max_iou_assign(anc, gl[b], labels[b, : num[b]], *thr, flags=flags)
+            assert np.array_equal(N(a)[b], ra), (thr, b)
+            assert np.array_equal(N(m)[b], rm) and np.array_equal(N(l)[b], rl)
+
+
+def test_assigner_cfg4_full_size_vs_c_oracle():
+    """BASELINE config 4b: 268 569 FPN anchors x 100 GTs, batch 2."""
+    from mxdetection_b200.core.anchor import AnchorGenerator, anchor_inside_flags, anchor_assign
+    d = syn.assigner_inputs(4, 2)
+    anchors, valid = [], []
+    for (fh, fw), s in zip(d["feat_shapes"], d["strides"]):
+        ag = AnchorGenerator(s, [8], [0.5, 1.0, 2.0])
+        anchors.append(ag.grid_anchors((fh, fw), s)); valid.append(ag.valid_flags((fh, fw), (fh, fw)))
+    anchors = torch.cat(anchors); valid = torch.cat(valid)
+    assert anchors.shape[0] == 268569
+    inside = anchor_inside_flags(anchors, valid, d["img_shape"], 0)
+    a, m, l = anchor_assign(anchors, inside, T(d["gts"]), T(d["num_gts"]), T(d["gt_labels"]))
+    ra, rm, rl = cref.max_iou_assign_batch(N(anchors), d["gts"], d["num_gts"], d["gt_labels"], N(inside))
+    assert np.array_equal(N(a), ra) and np.array_equal(N(m), rm) and np.array_equal(N(l), rl)
+    assert (ra > 0).sum() >= 200 and (ra == -1).sum() > 0
+
+
+# ================================================================== codec (Spec F) ==
+def test_codec_vs_oracle():
+    from mxdetection_b200.core.bbox import bbox2delta, delta2bbox
+    rng = np.random.default_rng(8)
+    p = syn.gt_boxes(rng, 800, 1344, 5000)
+    dl = rng.normal(0, 0.5, (5000, 4)).astype(F); dl[:50, 2:] *= 20
+    for stds, shape in [((1, 1, 1, 1), (800, 1344)), ((.1, .1, .2, .2), None)]:
+        ref = oracle.delta2bbox(p, dl, stds=stds, max_shape=shape)
+        got = N(delta2bbox(T(p), T(dl), stds=stds, max_shape=shape))
+        assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+        assert (got == ref).mean() > 0.9999
+    g = p + rng.uniform(-6, 6, p.shape).astype(F)
+    ref = oracle.bbox2delta(p, g, stds=(.1, .1, .2, .2))
+    got = N(bbox2delta(T(p), T(g), stds=(.1, .1, .2, .2)))
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-6) and (got == ref).mean() > 0.9999
+
+
+# ========================================================== RPN proposals (Spec H) ==
+def _run_rpn(d, cfgkw):
+    from mxdetection_b200.models.rpn_heads import RPNHead, ProposalConfig
+    head = RPNHead()
+    cfg = ProposalConfig(**cfgkw)
+    props, nv, handle = head.get_proposals([T(s) for s in d["scores"]], [T(x) for x in d["deltas"]], d["feat_shapes"],
+                                           d["img_shapes"], cfg, return_workspace=True)
+    B = d["scores"][0].shape[0]
+    stages = RPNHead.stages(handle, B)
+    return N(props), N(nv), [N(s) for s in stages]
+
+
+def _check_rpn_stagewise(d, cfgkw, props, nv, stages):
+    idx, boxes, keep, counts = stages
+    B = d["scores"][0].shape[0]
+    base = [oracle.gen_base_anchors(s, [8], [0.5, 1, 2]) for s in d["strides"]]
+    nms_pre, nms_post, max_num = cfgkw["nms_pre"], cfgkw["nms_post"], cfgkw["max_num"]
+    msz = cfgkw.get("min_bbox_size", 0)
+    for b in range(B):
+        cat = []
+        for l, (fh, fw) in enumerate(d["feat_shapes"]):
+            s = d["scores"][l][b]
+            ref_idx = oracle.topk_stable(s, nms_pre)
+            k = len(ref_idx)
+            assert counts[b, l, 0] == k
+            assert np.array_equal(idx[b, l, :k], ref_idx), "top-k indices must be bit-exact"       # stage 1
+            anc = oracle.grid_anchors(base[l], fh, fw, d["strides"][l])[ref_idx]
+            ref_boxes = oracle.delta2bbox(anc, d["deltas"][l][b][ref_idx], max_shape=tuple(d["img_shapes"][b]))
+            gb = boxes[b, l, :k]
+            assert np.abs(gb - ref_boxes).max() <= 1e-5 * 2000                                      # stage 2 (tolerance)
+            valid = None
+            if msz > 0:
+                valid = ((gb[:, 2] - gb[:, 0] + 1) >= msz) & ((gb[:, 3] - gb[:, 1] + 1) >= msz)
+            # stage 3: oracle NMS on the GPU-decoded boxes must give the GPU keep list, bit-exact
+            ref_keep = oracle.nms(gb, s[ref_idx], cfgkw["nms_thr"], delta=1.0, valid_mask=valid, max_out=nms_post)
+            nk = counts[b, l, 1]
+            assert nk == len(ref_keep) and np.array_equal(keep[b, l, :nk], ref_keep)
+            cat.append(np.concatenate([gb[ref_keep], s[ref_idx][ref_keep, None]], 1))
+        cat = np.concatenate(cat, 0)
+        if len(cat) > max_num:                                                                      # stage 4
+            cat = cat[stable_order_desc(cat[:, 4])[:max_num]]
+        assert nv[b] == len(cat)
+        assert np.array_equal(props[b, : len(cat)], cat) and np.all(props[b, len(cat):] == 0)
+
+
+@pytest.mark.parametrize("cfgkw", [dict(nms_pre=300, nms_post=100, max_num=150, nms_thr=0.7),
+                                   dict(nms_pre=2000, nms_post=1000, max_num=1000, nms_thr=0.7),
+                                   dict(nms_pre=500, nms_post=500, max_num=4000, nms_thr=0.5, min_bbox_size=20)])
+def test_rpn_proposals_small_stagewise_and_end_to_end(cfgkw):
+    d = syn.rpn_inputs(2, 3, 160, 224)
+    props, nv, stages = _run_rpn(d, cfgkw)
+    _check_rpn_stagewise(d, cfgkw, props, nv, stages)
+    base = [oracle.gen_base_anchors(s, [8], [0.5, 1, 2]) for s in d["strides"]]
+    ro, rn = oracle.rpn_proposals(d["scores"], d["deltas"], base, d["feat_shapes"], d["strides"], d["img_shapes"], **cfgkw)
+    assert np.array_equal(nv, rn)
+    assert np.abs(props - ro).max() <= 1e-5 * 2000 and (props == ro).mean() > 0.9999
+
+
+def test_rpn_proposals_cfg2_full_size():
+    """BASELINE config 2: 800x1088, 217 413 anchors/img, top-2000/level, NMS 0.7, post 1000, batch 2."""
+    cfgkw = dict(nms_pre=2000, nms_post=1000, max_num=1000, nms_thr=0.7)
+    d = syn.cfg2(batch=2)
+    assert sum(s.shape[1] for s in d["scores"]) == 217413
+    props, nv, stages = _run_rpn(d, cfgkw)
+    assert stages[3][:, :, 0].sum() == 2 * 8663
+    _check_rpn_stagewise(d, cfgkw, props, nv, stages)
+    base = [oracle.gen_base_anchors(s, [8], [0.5, 1, 2]) for s in d["strides"]]
+    ro, rn = cref.rpn_proposals(d["scores"], d["deltas"], base, d["feat_shapes"], d["strides"], d["img_shapes"], **cfgkw)
+    assert np.array_equal(nv, rn) and np.array_equal(props, ro)
+    assert np.all(props[:, :-1, 4] >= props[:, 1:, 4])           # sortedness of the truncated output
+
+
+def test_pipeline_is_cuda_graph_capturable():
+    """No allocation / sync inside the library: the whole proposal stage replays from a CUDA graph."""
+    from mxdetection_b200.models.rpn_heads import RPNHead, ProposalConfig
+    d = syn.rpn_inputs(2, 2, 160, 224)
+    head, cfg = RPNHead(), ProposalConfig(nms_pre=300, nms_post=100, max_num=150)
+    sc = [T(s) for s in d["scores"]]; dl = [T(x) for x in d["deltas"]]; shp = T(d["img_shapes"])
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        eager, _ = head.get_proposals(sc, dl, d["feat_shapes"], shp, cfg)
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            props, nv = head.get_proposals(sc, dl, d["feat_shapes"], shp, cfg)
+        props.zero_()
+        g.replay()
+        st.synchronize()
+    assert torch.equal(props, eager)

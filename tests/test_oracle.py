@@ -1,0 +1,223 @@
+"""CPU tests: the NumPy oracle against known-answer vectors
+and the committed torchvision golden fixtures; the C restatement against the NumPy oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import cref
+
+F = np.float32
+
+
+# ---------------------------------------------------------------- Spec A ----------
+@pytest.mark.parametrize("name", ["roi_align_a", "roi_align_b", "roi_align_c"])
+def test_roi_align_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    ps = tuple(int(v) for v in g["pooled"]); sc = float(g["scale"]); sr = int(g["sample_ratio"])
+    out = oracle.roi_align_forward(g["data"], g["rois"], ps, sc, sr)
+    assert np.array_equal(out, g["out"]), "forward must be bit-exact with the compiled cross-oracle"
+    gin = oracle.roi_align_backward(g["grad_out"], g["rois"], g["data"].shape, ps, sc, sr)
+    ref = g["grad_in"]
+    assert np.all(np.abs(gin - ref) <= 1e-4 * np.maximum(1, np.abs(ref)))   # bwd bar: 1e-4 (accumulation order)
+    # C restatement
+    assert np.array_equal(cref.roi_align_forward(g["data"], g["rois"], ps, sc, sr), g["out"])
+    gc = cref.roi_align_backward(g["grad_out"], g["rois"], g["data"].shape, ps, sc, sr)
+    assert np.all(np.abs(gc - ref) <= 1e-4 * np.maximum(1, np.abs(ref)))
+
+
+def test_roi_align_kat5_constant_and_ramp():
+    H, W = 40, 60
+    rois = np.array([[0, 20, 16, 150, 120], [0, 40.5, 33.25, 97.75, 80.5]], F)   # interior RoIs
+    const = np.full((1, 2, H, W), 3.25, F)
+    out = oracle.roi_align_forward(const, rois, (7, 7), 0.25, 2)
+    assert np.allclose(out, 3.25, rtol=0, atol=1e-6)
+    yy, xx = np.meshgrid(np.arange(H, dtype=F), np.arange(W, dtype=F), indexing="ij")
+    ramp = (0.5 * xx + 0.25 * yy)[None, None].astype(F)
+    out = oracle.roi_align_forward(ramp, rois, (7, 7), 0.25, 2)
+    for r in range(2):
+        x1, y1, x2, y2 = rois[r, 1:] * 0.25
+        bw = (x2 - x1) / 7; bh = (y2 - y1) / 7
+        cx = x1 + (np.arange(7) + 0.5) * bw; cy = y1 + (np.arange(7) + 0.5) * bh
+        expect = 0.5 * cx[None, :] + 0.25 * cy[:, None]      # ramp value at the bin centres
+        assert np.allclose(out[r, 0], expect, atol=1e-4)
+
+
+def test_roi_align_edge_cases():
+    data = np.random.default_rng(0).standard_normal((2, 3, 10, 12)).astype(F)
+    rois = np.array([[-1, 0, 0, 10, 10],        # negative batch -> zeros
+                     [0, -500, -500, -400, -400],  # far outside: every sample skipped -> zeros
+                     [1, 44, 36, 47.9, 39.9],      # bottom-right corner clamp
+                     [0, 5, 5, 5, 5]], F)          # degenerate: width clamps to 1
+    out = oracle.roi_align_forward(data, rois, (2, 2), 1.0, 2)
+    assert np.all(out[0] == 0) and np.all(out[1] == 0)
+    assert np.all(np.isfinite(out))
+    assert np.array_equal(out, cref.roi_align_forward(data, rois, (2, 2), 1.0, 2))
+    assert oracle.roi_align_forward(data, rois[:0], (2, 2), 1.0, 2).shape == (0, 3, 2, 2)
+
+
+# ---------------------------------------------------------------- Spec B ----------
+def test_box_nms_kat1_docstring():
+    x = np.array([[0, .5, .1, .1, .2, .2], [1, .4, .1, .1, .2, .2], [0, .3, .1, .1, .14, .14], [2, .6, .5, .5, .7, .8]], F)
+    out = oracle.box_nms_mx(x, overlap_thresh=0.1, coord_start=2, score_index=1, id_index=0, force_suppress=True)
+    exp = np.array([[2, .6, .5, .5, .7, .8], [0, .5, .1, .1, .2, .2], [-1] * 6, [-1] * 6], F)
+    assert np.array_equal(out, exp)
+    # class-aware: box1 (id 1) survives because only id-0 boxes suppress id-0 boxes
+    out2 = oracle.box_nms_mx(x, overlap_thresh=0.1, coord_start=2, score_index=1, id_index=0, force_suppress=False)
+    assert np.array_equal(out2[:3, 0], np.array([2, 0, 1], F)) and np.all(out2[3] == -1)
+
+
+@pytest.mark.parametrize("name", ["nms_a", "nms_b", "nms_c"])
+def test_nms_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    keep = oracle.nms(g["boxes"], g["scores"], float(g["thr"]), delta=0.0)
+    assert np.array_equal(keep, g["keep"])
+    assert np.array_equal(cref.nms(g["boxes"], g["scores"], float(g["thr"]), delta=0.0), g["keep"])
+    iou = oracle.bbox_overlaps(g["boxes"][:50], g["boxes"][:200], delta=0.0)
+    assert np.allclose(iou, g["iou_50x200"], rtol=0, atol=1e-6)
+
+
+def test_nms_ties_topk_validthresh():
+    boxes = np.array([[0, 0, 10, 10], [0, 0, 10, 10], [20, 20, 30, 30], [0, 0, 9, 9], [50, 50, 60, 60]], F)
+    scores = np.array([.5, .5, .5, .9, .1], F)
+    assert oracle.nms(boxes, scores, 0.5).tolist() == [3, 2, 4]               # 0 and 1 suppressed by 3
+    assert oracle.nms(boxes, scores, 0.9).tolist() == [3, 0, 2, 4]            # tie 0/1: lower index first, 1 == 0
+    assert oracle.nms(boxes, scores, 0.9, topk=2).tolist() == [3, 0]
+    assert oracle.nms(boxes, scores, 0.9, valid_thresh=0.1).tolist() == [3, 0, 2]
+    assert oracle.nms(boxes, scores, 0.9, max_out=1).tolist() == [3]
+    assert oracle.nms(boxes[:0], scores[:0], 0.5).tolist() == []
+
+
+# ---------------------------------------------------------------- Spec C ----------
+def test_anchors_kat2():
+    a = oracle.generate_anchors_mx(16, (8, 16, 32), (0.5, 1, 2))
+    assert a.shape == (9, 4)
+    assert a[0].tolist() == [-84, -40, 99, 55] and a[3].tolist() == [-56, -56, 71, 71]
+    assert a[-1].tolist() == [-168, -344, 183, 359]
+    b = oracle.gen_base_anchors(4, [8], [0.5, 1, 2])
+    assert b.tolist() == [[-21, -9, 24, 12], [-14, -14, 17, 17], [-9, -21, 12, 24]]
+
+
+def test_grid_anchor_counts_and_order():
+    from mxdetection_b200.synthetic import fpn_shapes
+    assert sum(h * w * 3 for h, w in fpn_shapes(800, 1088)) == 217413
+    assert sum(h * w * 3 for h, w in fpn_shapes(800, 1344)) == 268569
+    base = oracle.gen_base_anchors(8, [8], [0.5, 1, 2])
+    g = oracle.grid_anchors(base, 3, 5, 8)
+    assert g.shape == (45, 4)
+    assert np.array_equal(g[(2 * 5 + 4) * 3 + 1], base[1] + np.array([32, 16, 32, 16], F))
+    v = oracle.valid_flags(3, 5, 2, 4, 3)
+    assert v.reshape(3, 5, 3)[:, :, 0].tolist() == [[1, 1, 1, 1, 0], [1, 1, 1, 1, 0], [0, 0, 0, 0, 0]]
+    ins = oracle.inside_flags(g, np.ones(45, np.uint8), 24, 40, 0)
+    assert ins.sum() < 45 and np.array_equal(oracle.inside_flags(g, v, 24, 40, -1), v)
+
+
+# ------------------------------------------------------------ Specs D, E ----------
+def test_assign_kat4_tie_claimed_by_two_gts():
+    # anchor 2 has the same IoU with GT0 and GT1 and is the best anchor of both:
+    # per-anchor argmax picks the LOWER g (0), the low-quality loop lets the LATER g (1) override.
+    gts = np.array([[0, 0, 9, 9], [10, 0, 19, 9], [100, 100, 149, 149]], F)
+    anchors = np.array([[100, 100, 149, 149],   # == GT2 -> IoU 1 -> pos (3)
+                        [300, 300, 310, 310],   # no overlap -> neg (0)
+                        [5, 0, 14, 9],          # straddles GT0/GT1 equally (IoU 1/3 each)
+                        [100, 100, 149, 124],   # IoU .5 with GT2: between neg and pos -> ignore (-1)
+                        [0, 0, 9, 4],           # IoU .5 with GT0, not its max
+                        [400, 0, 409, 9]], F)
+    a, m, l = oracle.max_iou_assign(anchors, gts, np.array([7, 8, 9], np.int32), 0.7, 0.3, 0.3)
+    assert m[2] == oracle.bbox_overlaps(gts[:1], anchors[2:3])[0, 0] == oracle.bbox_overlaps(gts[1:2], anchors[2:3])[0, 0]
+    # GT0's best anchor is #4 (IoU .5), GT1's best is #2 (1/3): low-quality rule gives #4 -> 1, #2 -> 2
+    assert a.tolist() == [3, 0, 2, -1, 1, 0]
+    assert l.tolist() == [9, 0, 8, 0, 7, 0]
+    # remove anchor 4: now #2 is the best of BOTH GT0 and GT1 -> later g (2) wins
+    keep = [0, 1, 2, 3, 5]
+    a2, _, _ = oracle.max_iou_assign(anchors[keep], gts, None, 0.7, 0.3, 0.3)
+    assert a2.tolist() == [3, 0, 2, -1, 0]
+    # flags: excluded anchors neither receive labels nor feed gt_max
+    fl = np.array([1, 1, 0, 1, 1, 1], np.uint8)
+    a3, m3, _ = oracle.max_iou_assign(anchors, gts, None, 0.7, 0.3, 0.3, flags=fl)
+    assert a3[2] == -1 and m3[2] == 0 and a3[4] == 1
+    # G == 0 -> everything negative
+    a4, _, _ = oracle.max_iou_assign(anchors, gts[:0], None, 0.7, 0.3, 0.3)
+    assert np.all(a4 == 0)
+    c = cref.max_iou_assign_batch(anchors, gts[None], None, np.array([[7, 8, 9]], np.int32))
+    assert c[0][0].tolist() == a.tolist() and c[2][0].tolist() == l.tolist()
+
+
+def test_assign_c_vs_numpy_random():
+    rng = np.random.default_rng(5)
+    from mxdetection_b200.synthetic import gt_boxes
+    gts = gt_boxes(rng, 400, 600, 30)
+    base = oracle.gen_base_anchors(16, [8], [0.5, 1, 2])
+    anchors = oracle.grid_anchors(base, 25, 38, 16)
+    flags = oracle.inside_flags(anchors, np.ones(len(anchors), np.uint8), 400, 600, 0)
+    a = oracle.max_iou_assign(anchors, gts, rng.integers(1, 81, 30).astype(np.int32), 0.7, 0.3, 0.3, flags=flags)
+    c = cref.max_iou_assign_batch(anchors, gts[None], None, None, flags)
+    assert np.array_equal(a[0], c[0][0]) and np.array_equal(a[1], c[1][0])
+    assert (a[0] > 0).sum() >= 1
+
+
+# ------------------------------------------------------------ Specs F, G ----------
+def test_codec_roundtrip_and_clip():
+    rng = np.random.default_rng(3)
+    p = np.array([[10, 20, 110, 90], [0, 0, 15, 15], [300, 200, 420, 380]], F)
+    g = p + rng.uniform(-8, 8, p.shape).astype(F)
+    for stds in [(1, 1, 1, 1), (.1, .1, .2, .2)]:
+        d = oracle.bbox2delta(p, g, stds=stds)
+        back = oracle.delta2bbox(p, d, stds=stds)
+        assert np.abs(back - g).max() < 1e-3
+        assert np.array_equal(d, cref.bbox2delta(p, g, stds=stds))
+        assert np.array_equal(back, cref.delta2bbox(p, d, stds=stds))
+    big = np.array([[0, 0, 10, 10]], F); dl = np.array([[0, 0, 50, -50]], F)       # dw clamp at |log(16/1000)|
+    out = oracle.delta2bbox(big, dl)
+    assert np.isclose(out[0, 2] - out[0, 0] + 1, 11 * 1000 / 16, rtol=1e-5)
+    out = oracle.delta2bbox(big, dl, max_shape=(20, 30))
+    assert out[0, 0] == 0 and out[0, 2] == 29 and 0 <= out[0, 1] <= 19
+
+
+def test_levels_kat3_boundaries():
+    def roi(s):   # square of scale exactly s (x2-x1+1 = s)
+        return np.array([[0, 0, 0, s - 1, s - 1]], F)
+    assert oracle.map_roi_levels(roi(111), 4).tolist() == [0]
+    assert oracle.map_roi_levels(roi(112), 4).tolist() == [1]
+    assert oracle.map_roi_levels(roi(223), 4).tolist() == [1]
+    assert oracle.map_roi_levels(roi(224), 4).tolist() == [2]
+    assert oracle.map_roi_levels(roi(447), 4).tolist() == [2]
+    assert oracle.map_roi_levels(roi(448), 4).tolist() == [3]
+    assert oracle.map_roi_levels(roi(5000), 4).tolist() == [3]
+    assert oracle.map_roi_levels(roi(5000), 2).tolist() == [1]
+    rng = np.random.default_rng(9)
+    r = np.concatenate([np.zeros((500, 1)), rng.uniform(0, 600, (500, 2)), rng.uniform(600, 1300, (500, 2))], 1).astype(F)
+    assert np.array_equal(oracle.map_roi_levels(r, 4), cref.map_roi_levels(r, 4))
+    # libm-free form == exact floor(log2) away from the boundaries
+    w = r[:, 3] - r[:, 1] + 1; h = r[:, 4] - r[:, 2] + 1
+    lit = np.clip(np.floor(np.log2(np.sqrt(w.astype(np.float64) * h) / 56 + 1e-6)), 0, 3)
+    assert (oracle.map_roi_levels(r, 4) == lit).mean() > 0.99
+
+
+# ---------------------------------------------------------------- Spec H ----------
+def test_rpn_proposals_numpy_vs_c():
+    from mxdetection_b200.synthetic import rpn_inputs
+    d = rpn_inputs(2, 2, 160, 224)
+    base = [oracle.gen_base_anchors(s, [8], [0.5, 1, 2]) for s in d["strides"]]
+    cfg = dict(nms_pre=300, nms_thr=0.7, nms_post=100, max_num=150)
+    o, n = oracle.rpn_proposals(d["scores"], d["deltas"], base, d["feat_shapes"], d["strides"], d["img_shapes"], **cfg)
+    oc, nc = cref.rpn_proposals(d["scores"], d["deltas"], base, d["feat_shapes"], d["strides"], d["img_shapes"], **cfg)
+    assert np.array_equal(n, nc) and np.array_equal(o, oc)
+    assert n.max() == 150 and np.all(o[:, :, 4][:, :-1] >= o[:, :, 4][:, 1:])     # sorted when truncated
+    assert np.all(o[..., 0] >= 0) and np.all(o[..., 2] <= 223) and np.all(o[..., 3] <= 159)
+    # min-size filter drops rows
+    o2, n2 = oracle.rpn_proposals(d["scores"], d["deltas"], base, d["feat_shapes"], d["strides"], d["img_shapes"],
+                                  min_bbox_size=24, **cfg)
+    oc2, nc2 = cref.rpn_proposals(d["scores"], d["deltas"], base, d["feat_shapes"], d["strides"], d["img_shapes"],
+                                  min_bbox_size=24, **cfg)
+    assert np.array_equal(o2, oc2) and np.array_equal(n2, nc2)
+    w = o2[..., 2] - o2[..., 0] + 1
+    assert all(np.all(w[b, :n2[b]] >= 24) for b in range(2))
+
+
+def test_topk_stable_ties():
+    s = np.array([.5, .9, .5, .9, .1, .5], F)
+    assert oracle.topk_stable(s, 4).tolist() == [1, 3, 0, 2]
+    assert oracle.topk_stable(s, 100).tolist() == [1, 3, 0, 2, 5, 4]
