@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the mxdetection detection hot path on B200.
+
+Metric (BASELINE.json): RoIAlign RoIs/s fwd+bwd, with proposals/s, assigner anchors/s and the HBM
+roofline fraction beside it.  Workload at N GPUs (weak scaling): every rank owns 8 images of BASELINE
+config 3 / 5 - the Faster R-CNN R50-FPN RoI stage, 512 RoIs/img x 8 imgs on 4 FPN maps of an
+800x1344 image, 256 ch, 7x7, sample_ratio 2 - whose 731 MB of feature maps exceed the 126 MB L2, so
+every step streams from HBM.  A step = one forward + one backward of that shard.
+
+  python bench.py --gpus N --steps K --warmup W           (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference ...                    (the CPU port of the reference path, timed)
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier +
+synchronize on both sides of the K timed steps, max over ranks.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+F = np.float32
+METRIC = "roialign_fpn_fwd_bwd_rois_per_s"
+UNIT = "RoIs/s"
+IMGS_PER_GPU = 8
+ROIS_PER_IMG = 512
+POOLED = (7, 7)
+WORKLOAD = ("BASELINE config 3 (= per-GPU shard of config 5): FPN RoI stage, 8 imgs x 512 RoIs, 800x1344 "
+            "(1333x800 padded), 4 levels x 256 ch fp32 NCHW, 7x7, sample_ratio 2, level assignment in-kernel")
+
+
+def config_dict(n_gpus):
+    return {"workload": WORKLOAD, "images_per_gpu": IMGS_PER_GPU, "rois_per_image": ROIS_PER_IMG,
+            "global_images": IMGS_PER_GPU * n_gpus, "parallelism": "dp%d (images sharded, no data-path collective)" % n_gpus,
+            "l2_policy": "inputs larger than L2 (731 MB maps + 206 MB grad_out per step vs 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------ helpers --
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock / throttle-reason sampling DURING the timed region (NVML polled from a thread every ~2 ms;
+    same fields as the nvidia-smi recipe of B200_PROFILING.md, which is too slow to start for a 50 ms region)."""
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, torch_device_index):
+        import threading
+        self.samples, self.reasons, self.power = [], set(), []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.max_mhz = None
+        self.err = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(torch_device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+        except Exception as e:  # no NVML: report it instead of inventing clocks
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception as e:
+                self.err = repr(e)
+                return
+            time.sleep(0.002)
+
+    def start(self):
+        if self.thread is not None:
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        out = {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "power_w_max": max(self.power) if self.power else None, "samples": len(self.samples),
+               "reasons": sorted(self.reasons)}
+        if self.err:
+            out["error"] = self.err
+        return out
+
+
+def touched_bytes(rois, levels, shapes, scales, nimg, channels, pooled, sr):
+    """Unique feature pixels any tap reads (Spec A sample positions), times C*4 bytes - the tighter
+    algorithmic-bytes variant of SURVEY.md 8(d).  Accounting only; not on the product path."""
+    PH, PW = pooled
+    masks = [np.zeros((nimg, h, w), bool) for h, w in shapes]
+
+    def axis(start, binsz, P, size):
+        t = np.arange(P * sr)
+        c = (start + (t // sr).astype(F) * binsz) + (((t % sr).astype(F) + F(0.5)) * binsz) / F(sr)
+        ok = ~((c < -1) | (c > size))
+        c = np.maximum(c, 0)
+        lo = np.minimum(c.astype(np.int64), size - 1)
+        hi = np.minimum(lo + 1, size - 1)
+        return np.unique(np.concatenate([lo[ok], hi[ok]]))
+
+    for r, lv in zip(rois, levels):
+        b = int(r[0]); sc = F(scales[lv]); H, W = shapes[lv]
+        x1, y1, x2, y2 = [F(v) * sc for v in r[1:]]
+        bw = max(x2 - x1, F(1)) / F(PW); bh = max(y2 - y1, F(1)) / F(PH)
+        rows = axis(y1, bh, PH, H); cols = axis(x1, bw, PW, W)
+        if len(rows) and len(cols):
+            masks[lv][b][np.ix_(rows, cols)] = True
+    return int(sum(int(m.sum()) for m in masks)) * channels * 4
+
+
+# ------------------------------------------------------------------ reference arm --
+def cpu_reference_fpn(n_images, passes, first_image=0):
+    """Times the C port of the reference CPU path (oracle/cpu_ref.c: OpenMP-over-RoIs forward, serial
+    backward - the parallelisation of mxnet 1.3's roi_align.cc) on `n_images` images of the workload."""
+    from oracle import cref
+    from mxdetection_b200 import synthetic as syn
+    d = syn.cfg3(batch=n_images, first_image=first_image, with_features=True)
+    lv = cref.map_roi_levels(d["rois"], 4)
+    shapes = [f.shape for f in d["feats"]]
+    times = []
+    for _ in range(passes):
+        t0 = time.perf_counter()
+        cref.roi_align_forward(d["feats"], d["rois"], POOLED, d["scales"], 2, lv)
+        cref.roi_align_backward(d["grad_out"], d["rois"], shapes, POOLED, d["scales"], 2, lv)
+        times.append(time.perf_counter() - t0)
+    return n_images * ROIS_PER_IMG, times, cref.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    rois, times, threads = cpu_reference_fpn(1, args.warmup + args.steps)
+    times = times[args.warmup:]
+    total = sum(times)
+    value = rois * len(times) / total
+    sample = ("each step = 1 of the 8 images per GPU (512 RoIs, 4 FPN maps x 256 ch): C port of the mxnet-1.3 "
+              "CPU ROIAlign (oracle/cpu_ref.c), forward OpenMP over RoIs, backward serial")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "host_cpus": os.cpu_count()}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------ our arm --
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import mxdetection_b200 as m
+    from mxdetection_b200 import synthetic as syn
+    from mxdetection_b200.ops import (roi_align_backward, roi_align_forward, roi_align_fpn_backward,
+                                      roi_align_fpn_forward)
+    from mxdetection_b200.core.anchor import AnchorGenerator, anchor_assign, anchor_inside_flags
+    from mxdetection_b200.models.roi_extractors import map_roi_levels
+    from mxdetection_b200.models.rpn_heads import ProposalConfig, RPNHead
+    from mxdetection_b200.parallel import gather_detections
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, max(args.warmup, 3)
+    first_image = rank * IMGS_PER_GPU
+    peak_gbs, peak_src = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    # ---------------- workload (synthetic, resident in HBM for `value`) ----------------
+    d = syn.cfg3(batch=IMGS_PER_GPU, first_image=first_image, with_features=False)
+    shapes = [(IMGS_PER_GPU, 256, h, w) for h, w in d["feat_shapes"]]
+    gen = torch.Generator(device=dev); gen.manual_seed(1000 * 3 + rank)
+    feats = [torch.randn(s, device=dev, generator=gen) for s in shapes]
+    R = d["rois"].shape[0]
+    rois = torch.from_numpy(d["rois"]).to(dev)
+    grad_out = torch.randn((R, 256) + POOLED, device=dev, generator=gen)
+    out = torch.empty((R, 256) + POOLED, device=dev)
+    grads = [torch.empty(s, device=dev) for s in shapes]
+    scales = d["scales"]
+
+    def fwd():
+        roi_align_fpn_forward(feats, rois, POOLED, scales, 2, out=out)
+
+    def bwd():
+        roi_align_fpn_backward(grad_out, rois, shapes, POOLED, scales, 2, grad_feats=grads, accumulate=False)
+
+    for _ in range(Wm):
+        fwd(); bwd()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    launches0 = m.launch_count()
+    marks = [(ev(), ev(), ev()) for _ in range(K)]
+    barrier()
+    for a, b, c in marks:
+        a.record(); fwd(); b.record(); bwd(); c.record()
+    barrier()
+    launches = m.launch_count() - launches0
+    clocks = sampler.stop()
+    total_ms = marks[0][0].elapsed_time(marks[-1][2])
+    fwd_ms = statistics.mean(a.elapsed_time(b) for a, b, _ in marks)
+    bwd_ms = statistics.mean(b.elapsed_time(c) for _, b, c in marks)
+    total_ms = max_over_ranks(total_ms)
+    value = world * R * K / (total_ms * 1e-3)
+
+    # ---------------- roofline of the dominant kernel ----------------
+    levels = map_roi_levels(rois, 4).cpu().numpy()
+    map_bytes = sum(int(np.prod(s)) * 4 for s in shapes)
+    out_bytes = R * 256 * POOLED[0] * POOLED[1] * 4
+    tb = touched_bytes(d["rois"], levels, d["feat_shapes"], scales, IMGS_PER_GPU, 256, POOLED, 2)
+    alg_fwd = min(map_bytes, tb) + out_bytes          # read maps (or only the touched pixels) + write out
+    alg_bwd = out_bytes + map_bytes                   # read grad_out + write every grad-map byte (req=write)
+    dom = "roi_align_backward" if bwd_ms >= fwd_ms else "roi_align_forward"
+    dom_ms = max(fwd_ms, bwd_ms); dom_bytes = alg_bwd if bwd_ms >= fwd_ms else alg_fwd
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes": dom_bytes, "avg_ms": dom_ms,
+                "forward": {"ms": fwd_ms, "bytes": alg_fwd, "gbs": alg_fwd / fwd_ms / 1e6, "frac": alg_fwd / fwd_ms / 1e6 / peak_gbs,
+                            "map_bytes": map_bytes, "touched_bytes": tb},
+                "backward": {"ms": bwd_ms, "bytes": alg_bwd, "gbs": alg_bwd / bwd_ms / 1e6, "frac": alg_bwd / bwd_ms / 1e6 / peak_gbs,
+                             "note": "includes the req=write zero-fill of the grad maps"},
+                "fwd_bwd": {"bytes": alg_fwd + alg_bwd, "gbs": (alg_fwd + alg_bwd) / (fwd_ms + bwd_ms) / 1e6,
+                            "frac": (alg_fwd + alg_bwd) / (fwd_ms + bwd_ms) / 1e6 / peak_gbs}}
+
+    # ---------------- e2e: host buffers through the public API, copies inside the timed region ----
+    e_steps = max(1, min(K, args.e2e_steps))
+    feats_h = [torch.empty(s, pin_memory=True).normal_() for s in shapes]
+    gout_h = torch.empty(tuple(grad_out.shape), pin_memory=True).normal_()
+    rois_h = torch.from_numpy(d["rois"]).pin_memory()
+    out_h = torch.empty(tuple(out.shape), pin_memory=True)
+    grads_h = [torch.empty(s, pin_memory=True) for s in shapes]
+    h2d = sum(t.numel() * 4 for t in feats_h) + gout_h.numel() * 4 + rois_h.numel() * 4
+    d2h = out_h.numel() * 4 + sum(t.numel() * 4 for t in grads_h)
+
+    def e2e_step():
+        for dst, src in zip(feats, feats_h):
+            dst.copy_(src, non_blocking=True)
+        rois.copy_(rois_h, non_blocking=True)
+        grad_out.copy_(gout_h, non_blocking=True)
+        fwd(); bwd()
+        out_h.copy_(out, non_blocking=True)
+        for dst, src in zip(grads_h, grads):
+            dst.copy_(src, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e = {"value": world * R * e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": e_steps, "ms_per_step": e2e_ms / e_steps,
+           "api": "mxdetection_b200.ops.roi_align_fpn_forward/backward (ctypes C ABI), pinned host buffers"}
+    del feats_h, gout_h, grads_h, out_h
+
+    # ---------------- secondary metrics of BASELINE.json (each: events, max over ranks) ----------
+    def timed(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        barrier()
+        es = [(ev(), ev()) for _ in range(iters)]
+        for a, b in es:
+            a.record(); fn(); b.record()
+        barrier()
+        return max_over_ranks(statistics.mean(a.elapsed_time(b) for a, b in es))
+
+    secondary = {}
+    if not args.no_secondary:
+        it = args.secondary_iters
+        # (a) config 1: 512 RoIs on one 256x200x272 map; 4 rotating buffer sets so the map is never L2-resident
+        c1 = syn.cfg1()
+        rois1 = torch.from_numpy(c1["rois"]).to(dev)
+        maps1 = [torch.randn((1, 256, 200, 272), device=dev, generator=gen) for _ in range(4)]
+        g1 = [torch.empty((1, 256, 200, 272), device=dev) for _ in range(4)]
+        go1 = [torch.randn((512, 256, 7, 7), device=dev, generator=gen) for _ in range(4)]
+        o1 = [torch.empty((512, 256, 7, 7), device=dev) for _ in range(4)]
+        ctr = [0]
+
+        def cfg1_step():
+            i = ctr[0] % 4; ctr[0] += 1
+            roi_align_forward(maps1[i], rois1, (7, 7), 0.25, 2, out=o1[i])
+            roi_align_backward(go1[i], rois1, (1, 256, 200, 272), (7, 7), 0.25, 2, grad_data=g1[i])
+        ms = timed(cfg1_step, 4 * max(it // 4, 2))
+        b1 = 2 * (55705600 + 25690112)
+        secondary["cfg1_roialign_fwd_bwd"] = {"rois_per_s": world * 512 / (ms * 1e-3), "ms": ms,
+                                              "hbm_frac": b1 / ms / 1e6 / peak_gbs, "algorithmic_bytes": b1,
+                                              "l2_policy": "4 rotating buffer sets (445 MB) > L2"}
+        del maps1, g1, go1, o1
+        # (b) config 2: RPN proposals, 800x1088, 217 413 anchors/img, batch 2 - and the 8-image shard
+        head, pcfg = RPNHead(), ProposalConfig(nms_pre=2000, nms_post=1000, max_num=1000, nms_thr=0.7)
+        for name, bsz, (ih, iw) in (("cfg2_rpn_proposals_b2", 2, (800, 1088)), ("cfg5_rpn_proposals_b8", 8, (800, 1344))):
+            r = syn.rpn_inputs(2, bsz, ih, iw, first_image=first_image)
+            sc = [torch.from_numpy(s).to(dev) for s in r["scores"]]; dl = [torch.from_numpy(x).to(dev) for x in r["deltas"]]
+            shp = torch.from_numpy(r["img_shapes"]).to(dev)
+            nv = [None]
+
+            def prop_step():
+                nv[0] = head.get_proposals(sc, dl, r["feat_shapes"], shp, pcfg)
+            ms = timed(prop_step, it)
+            n_anchor = sum(s.shape[1] for s in sc)
+            bytes_ = bsz * (n_anchor * 4 + 8663 * 16 + 1000 * 20)
+            secondary[name] = {"images_per_s": world * bsz / (ms * 1e-3), "input_anchors_per_s": world * bsz * n_anchor / (ms * 1e-3),
+                               "output_proposals_per_s": world * float(nv[0][1].sum().item()) / (ms * 1e-3), "ms": ms,
+                               "hbm_frac": bytes_ / ms / 1e6 / peak_gbs, "bound": "latency (dependent sort/NMS chain), not HBM"}
+            if bsz == 8:
+                pipe_prop = (sc, dl, r["feat_shapes"], shp)
+        # (c) config 4b: max-IoU assigner, 268 569 anchors x 100 GT, 8 images
+        a = syn.assigner_inputs(4, IMGS_PER_GPU, first_image=first_image)
+        anchors, valid = [], []
+        for (fh, fw), s in zip(a["feat_shapes"], a["strides"]):
+            ag = AnchorGenerator(s, [8], [0.5, 1.0, 2.0])
+            anchors.append(ag.grid_anchors((fh, fw), s, device=dev)); valid.append(ag.valid_flags((fh, fw), (fh, fw), device=dev))
+        anchors = torch.cat(anchors); inside = anchor_inside_flags(anchors, torch.cat(valid), a["img_shape"], 0)
+        gts = torch.from_numpy(a["gts"]).to(dev); ngt = torch.from_numpy(a["num_gts"]).to(dev); gl = torch.from_numpy(a["gt_labels"]).to(dev)
+
+        def assign_step():
+            anchor_assign(anchors, inside, gts, ngt, gl)
+        ms = timed(assign_step, it)
+        pairs = IMGS_PER_GPU * anchors.shape[0] * 100
+        secondary["cfg4b_max_iou_assigner_b8"] = {"anchors_per_s": world * IMGS_PER_GPU * anchors.shape[0] / (ms * 1e-3), "ms": ms,
+                                                   "gt_anchor_pairs_per_s": world * pairs / (ms * 1e-3),
+                                                   "fp32_alu_frac_est": 2 * 20.0 * pairs / (ms * 1e-3) / 74.4e12,
+                                                   "hbm_frac": IMGS_PER_GPU * anchors.shape[0] * 28 / ms / 1e6 / peak_gbs,
+                                                   "bound": "fp32 ALU (two passes x ~20 flop/pair), not HBM"}
+        # (d) config 4a: mask branch, 14x14 on 128 RoIs/img x 8 imgs (same maps)
+        dm = syn.cfg4_mask(batch=IMGS_PER_GPU, first_image=first_image, with_features=False)
+        rois_m = torch.from_numpy(dm["rois"]).to(dev)
+        go_m = torch.randn((rois_m.shape[0], 256, 14, 14), device=dev, generator=gen); o_m = torch.empty_like(go_m)
+
+        def mask_step():
+            roi_align_fpn_forward(feats, rois_m, (14, 14), scales, 2, out=o_m)
+            roi_align_fpn_backward(go_m, rois_m, shapes, (14, 14), scales, 2, grad_feats=grads)
+        ms = timed(mask_step, max(it // 2, 3))
+        bm = 2 * (map_bytes + o_m.numel() * 4)
+        secondary["cfg4a_mask_roialign_14x14_b8"] = {"rois_per_s": world * rois_m.shape[0] / (ms * 1e-3), "ms": ms,
+                                                      "hbm_frac": bm / ms / 1e6 / peak_gbs, "algorithmic_bytes": bm}
+        # (e) config 5 shard pipeline: assigner + proposals + RoI stage fwd/bwd (+ NCCL gather of detections at N>1)
+        def pipeline_step():
+            anchor_assign(anchors, inside, gts, ngt, gl)
+            p, n = head.get_proposals(pipe_prop[0], pipe_prop[1], pipe_prop[2], pipe_prop[3], pcfg)
+            fwd(); bwd()
+            gather_detections(p, n, first_image)
+        ms = timed(pipeline_step, max(it // 2, 3))
+        secondary["cfg5_shard_pipeline"] = {"images_per_s": world * IMGS_PER_GPU / (ms * 1e-3), "ms": ms,
+                                            "stages": "assigner + rpn proposals + fpn roialign fwd/bwd + detection all-gather"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (N(0,1) features / grads, COCO-shaped RoIs, seeded per image)",
+            "config": config_dict(world), "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
+            "launches_per_step": launches / K, "clocks": clocks, "secondary": secondary}
+
+    # ---------------- CPU baseline (rank 0, N=1 only): bounded sample of the same workload --------
+    if world == 1 and not args.no_cpu_baseline:
+        n_rois, times, threads = cpu_reference_fpn(2, 3, first_image)
+        t = sum(times[1:]) / len(times[1:])
+        line["cpu_baseline"] = {"value": n_rois / t, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "2 of the 8 images (1024 RoIs) of the same workload, best-effort 2 timed passes after 1 warm-up: "
+                                          "oracle/cpu_ref.c, forward OpenMP over RoIs, backward serial (mxnet 1.3 roi_align.cc structure)",
+                                "seconds_per_pass": t, "host_cpus": os.cpu_count()}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--secondary-iters", type=int, default=20)
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

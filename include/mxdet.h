@@ -53,15 +53,21 @@ uint64_t mxd_launch_count(void);      /* kernels enqueued by this library so far
  *      contract mx.nd.contrib.ROIAlign + _backward_ROIAlign, mxnet 1.3.0
  *      /root/reference/README.md:37; Spec A) -------------------------------- */
 /* data (N,C,H,W) f32; rois (R,5) f32 [b,x1,y1,x2,y2]; out (R,C,PH,PW) f32.     */
+/* Workspace for the plane-resident kernels (shared-memory resident row bands of
+ * the feature planes).  workspace == NULL selects the gather
+ * kernels (same results, slower).  feat_h/feat_w: host int[num_levels].          */
+size_t mxd_roi_align_workspace_bytes(int num_rois, int batch, int channels, int num_levels,
+                                     const int* feat_h, const int* feat_w,
+                                     int pooled_h, int pooled_w, int sample_ratio);
 int mxd_roi_align_forward(const DLTensor* data, const DLTensor* rois, DLTensor* out,
                           int pooled_h, int pooled_w, float spatial_scale, int sample_ratio,
-                          void* stream);
+                          void* workspace, size_t workspace_bytes, void* stream);
 /* grad_out (R,C,PH,PW); grad_data (N,C,H,W).  accumulate=0: req='write'
  * (grad_data is zero-filled first); accumulate=1: req='add'.  grad wrt rois is
  * identically zero and not produced.                                            */
 int mxd_roi_align_backward(const DLTensor* grad_out, const DLTensor* rois, DLTensor* grad_data,
                            int pooled_h, int pooled_w, float spatial_scale, int sample_ratio,
-                           int accumulate, void* stream);
+                           int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- G1/G2  FPN level assignment + multi-level RoI extraction
  *      (mxdetection/models/roi_extractors, /root/reference/README.md:32;
@@ -75,12 +81,12 @@ int mxd_roi_align_fpn_forward(const DLTensor* const* feats, int num_levels,
                               const float* spatial_scales, const DLTensor* rois,
                               const DLTensor* levels, DLTensor* out,
                               int pooled_h, int pooled_w, int sample_ratio, float finest_scale,
-                              void* stream);
+                              void* workspace, size_t workspace_bytes, void* stream);
 int mxd_roi_align_fpn_backward(const DLTensor* grad_out, const DLTensor* rois,
                                const DLTensor* levels, DLTensor* const* grad_feats,
                                int num_levels, const float* spatial_scales,
                                int pooled_h, int pooled_w, int sample_ratio, float finest_scale,
-                               int accumulate, void* stream);
+                               int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- B1  NMS  (mxdetection/ops, /root/reference/README.md:24; contract
  *      mx.nd.contrib.box_nms, Spec B: strict iou > thr, stable score-desc /

@@ -152,11 +152,13 @@ def require_cuda(*tensors):
 # ---- argtypes (explicit so that Python floats become C floats, not doubles) ----
 _P = c_void_p
 _SIG = {
-    "mxd_roi_align_forward": [_P, _P, _P, c_int, c_int, c_float, c_int, _P],
-    "mxd_roi_align_backward": [_P, _P, _P, c_int, c_int, c_float, c_int, c_int, _P],
+    "mxd_roi_align_workspace_bytes": [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_int, c_int, c_int],
+    "mxd_roi_align_forward": [_P, _P, _P, c_int, c_int, c_float, c_int, _P, c_size_t, _P],
+    "mxd_roi_align_backward": [_P, _P, _P, c_int, c_int, c_float, c_int, c_int, _P, c_size_t, _P],
     "mxd_map_roi_levels": [_P, _P, c_int, c_float, _P],
-    "mxd_roi_align_fpn_forward": [_P, c_int, POINTER(c_float), _P, _P, _P, c_int, c_int, c_int, c_float, _P],
-    "mxd_roi_align_fpn_backward": [_P, _P, _P, _P, c_int, POINTER(c_float), c_int, c_int, c_int, c_float, c_int, _P],
+    "mxd_roi_align_fpn_forward": [_P, c_int, POINTER(c_float), _P, _P, _P, c_int, c_int, c_int, c_float, _P, c_size_t, _P],
+    "mxd_roi_align_fpn_backward": [_P, _P, _P, _P, c_int, POINTER(c_float), c_int, c_int, c_int, c_float, c_int, _P,
+                                   c_size_t, _P],
     "mxd_topk_stable_workspace_bytes": [c_int, c_int, c_int],
     "mxd_topk_stable": [_P, _P, _P, c_int, _P, c_size_t, _P],
     "mxd_nms_workspace_bytes": [c_int, c_int],

@@ -244,7 +244,6 @@ int mxd_max_iou_assign(const DLTensor* anchors, const DLTensor* gts, const DLTen
   a.gt_max = static_cast<unsigned int*>(workspace);
   a.pos = pos_iou_thr; a.neg = neg_iou_thr; a.min_pos = min_pos_iou; a.delta = delta;
   MXD_CUDA_OK(cudaMemsetAsync(a.gt_max, 0, need, st));
-  count_launch();
   dim3 grid(((int)N + kAssignThreads - 1) / kAssignThreads, B);
   assign_pass1_kernel<<<grid, kAssignThreads, 0, st>>>(a);
   MXD_POST_LAUNCH("assign_pass1");

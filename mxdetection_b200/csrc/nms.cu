@@ -274,8 +274,7 @@ int mxd_nms(const DLTensor* boxes, const DLTensor* scores, const DLTensor* ids, 
   const int cap = (int)keep->shape[0];
   if (n == 0 || cap == 0) {
     MXD_CUDA_OK(cudaMemsetAsync(dptr<int>(num_keep), 0, sizeof(int), st));
-    count_launch();
-    return MXD_OK;
+      return MXD_OK;
   }
   MXD_REQUIRE(k <= MXD_SORT_CAP, MXD_ENOTSUP,
               "NMS over %d rows exceeds the in-CTA sort capacity %d (pass topk)", k, MXD_SORT_CAP);
@@ -366,7 +365,6 @@ int mxd_box_nms_backward(const DLTensor* out_grad, const DLTensor* index, DLTens
   if (B == 0 || N == 0) return MXD_OK;
   cudaStream_t st = as_stream(stream);
   MXD_CUDA_OK(cudaMemsetAsync(dptr<float>(in_grad), 0, sizeof(float) * (size_t)numel(in_grad), st));
-  count_launch();
   dim3 g((N + 255) / 256, B);
   boxnms_backward_kernel<<<g, 256, 0, st>>>(dptr<float>(out_grad), dptr<int>(index), N, K, dptr<float>(in_grad));
   MXD_POST_LAUNCH("boxnms_backward");

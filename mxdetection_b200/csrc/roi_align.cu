@@ -9,84 +9,12 @@
 // tables (index, weights, validity) are computed once per CTA in shared
 // memory - they are shared by every channel - then each thread produces
 // outputs (c, ph, pw) with coalesced stores and read-only-path tap loads.
-#include "common.cuh"
+#include "roi_align.cuh"
 
 namespace mxd {
 
-struct FpnDesc {
-  float* feat[MXD_MAX_LEVELS];
-  int H[MXD_MAX_LEVELS];
-  int W[MXD_MAX_LEVELS];
-  float scale[MXD_MAX_LEVELS];
-  int num_levels;
-  int N, C;
-};
-
 constexpr int kTab = 64;       // max samples per axis held in the smem tables
 constexpr int kThreads = 256;
-
-struct AxisTap {
-  int lo, hi;      // element offsets along the axis (already multiplied by the pitch)
-  float l, h;      // weights of hi / lo taps
-  int valid;
-};
-
-// One sample coordinate of Spec A along one axis.  `pitch` = 1 for x, W for y.
-__device__ __forceinline__ AxisTap axis_tap(float start, float bin, int grid, int p, int i, int size,
-                                            int pitch) {
-  AxisTap t;
-  // c = (start + p*bin) + ((i+.5f)*bin)/grid   -- order of Spec A
-  float c = __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)),
-                      __fdiv_rn(__fmul_rn(__fadd_rn((float)i, 0.5f), bin), (float)grid));
-  t.valid = !(c < -1.0f || c > (float)size);
-  if (c <= 0.0f) c = 0.0f;
-  int lo = t.valid ? (int)c : 0;
-  int hi;
-  if (lo >= size - 1) {
-    hi = lo = size - 1;
-    c = (float)lo;
-  } else {
-    hi = lo + 1;
-  }
-  t.l = __fsub_rn(c, (float)lo);
-  t.h = __fsub_rn(1.0f, t.l);
-  t.lo = lo * pitch;
-  t.hi = hi * pitch;
-  return t;
-}
-
-struct RoiGeom {
-  int b, lvl, H, W, gh, gw;
-  float rsw, rsh, bh, bw;
-  float* plane0;  // feat[lvl] + b*C*H*W
-  bool ok;
-};
-
-__device__ __forceinline__ RoiGeom roi_geom(const FpnDesc& d, const float* __restrict__ rois,
-                                            const int* __restrict__ levels, int n, int PH, int PW,
-                                            int sr, float finest) {
-  RoiGeom g;
-  const float* r = rois + (size_t)n * 5;
-  float rb = r[0], x1 = r[1], y1 = r[2], x2 = r[3], y2 = r[4];
-  g.b = (int)rb;
-  g.lvl = 0;
-  if (d.num_levels > 1) g.lvl = levels ? levels[n] : roi_level(x1, y1, x2, y2, d.num_levels, finest);
-  g.ok = g.b >= 0 && g.b < d.N && g.lvl >= 0 && g.lvl < d.num_levels;
-  int lv = g.ok ? g.lvl : 0;
-  g.H = d.H[lv];
-  g.W = d.W[lv];
-  float sc = d.scale[lv];
-  g.rsw = __fmul_rn(x1, sc);
-  g.rsh = __fmul_rn(y1, sc);
-  float rew = __fmul_rn(x2, sc), reh = __fmul_rn(y2, sc);
-  float rw = fmaxf(__fsub_rn(rew, g.rsw), 1.0f), rh = fmaxf(__fsub_rn(reh, g.rsh), 1.0f);
-  g.bh = __fdiv_rn(rh, (float)PH);
-  g.bw = __fdiv_rn(rw, (float)PW);
-  g.gh = sr > 0 ? sr : (int)ceilf(g.bh);
-  g.gw = sr > 0 ? sr : (int)ceilf(g.bw);
-  g.plane0 = d.feat[lv] + (size_t)(g.ok ? g.b : 0) * d.C * g.H * g.W;
-  return g;
-}
 
 template <bool BWD, bool TAB>
 __global__ void __launch_bounds__(kThreads)
@@ -209,6 +137,7 @@ static int build_desc(const DLTensor* const* feats, int L, const float* scales, 
     MXD_REQUIRE(feats[l]->shape[2] >= 1 && feats[l]->shape[3] >= 1 &&
                 feats[l]->shape[2] * feats[l]->shape[3] < (1ll << 31), MXD_EINVAL, "%s: bad H,W", what);
     d->feat[l] = dptr<float>(feats[l]);
+    MXD_REQUIRE(((uintptr_t)d->feat[l] & 3) == 0, MXD_EINVAL, "%s: misaligned data", what);
     d->H[l] = (int)feats[l]->shape[2];
     d->W[l] = (int)feats[l]->shape[3];
     d->scale[l] = scales[l];
@@ -239,45 +168,64 @@ using namespace mxd;
 
 extern "C" {
 
+size_t mxd_roi_align_workspace_bytes(int num_rois, int batch, int channels, int num_levels, const int* feat_h,
+                                     const int* feat_w, int pooled_h, int pooled_w, int sample_ratio) {
+  if (num_levels < 1 || num_levels > MXD_MAX_LEVELS || !feat_h || !feat_w) return 0;
+  return plane_workspace_bytes(num_rois, batch, num_levels, feat_h, feat_w, channels, pooled_h, pooled_w, sample_ratio);
+}
+
 int mxd_roi_align_fpn_forward(const DLTensor* const* feats, int num_levels, const float* spatial_scales,
                               const DLTensor* rois, const DLTensor* levels, DLTensor* out,
                               int pooled_h, int pooled_w, int sample_ratio, float finest_scale,
-                              void* stream) {
+                              void* workspace, size_t workspace_bytes, void* stream) {
   FpnDesc d; int dev = -1, R = 0, rc;
   if ((rc = build_desc(feats, num_levels, spatial_scales, &d, &dev, "feats"))) return rc;
   if ((rc = check_common(rois, levels, out, d.C, pooled_h, pooled_w, &dev, &R))) return rc;
-  return launch_gather<false>(d, dptr<float>(rois), levels ? dptr<int>(levels) : nullptr, dptr<float>(out),
-                              R, pooled_h, pooled_w, sample_ratio, finest_scale, as_stream(stream));
+  const int* lv = levels ? dptr<int>(levels) : nullptr;
+  if (workspace) {
+    int handled = 0;
+    if ((rc = plane_forward(d, dptr<float>(rois), lv, dptr<float>(out), R, pooled_h, pooled_w, sample_ratio,
+                            finest_scale, workspace, workspace_bytes, as_stream(stream), &handled))) return rc;
+    if (handled) return MXD_OK;
+  }
+  return launch_gather<false>(d, dptr<float>(rois), lv, dptr<float>(out), R, pooled_h, pooled_w, sample_ratio,
+                              finest_scale, as_stream(stream));
 }
 
 int mxd_roi_align_fpn_backward(const DLTensor* grad_out, const DLTensor* rois, const DLTensor* levels,
                                DLTensor* const* grad_feats, int num_levels, const float* spatial_scales,
                                int pooled_h, int pooled_w, int sample_ratio, float finest_scale,
-                               int accumulate, void* stream) {
+                               int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
   FpnDesc d; int dev = -1, R = 0, rc;
   if ((rc = build_desc(grad_feats, num_levels, spatial_scales, &d, &dev, "grad_feats"))) return rc;
   if ((rc = check_common(rois, levels, grad_out, d.C, pooled_h, pooled_w, &dev, &R))) return rc;
   cudaStream_t st = as_stream(stream);
+  const int* lv = levels ? dptr<int>(levels) : nullptr;
+  if (workspace) {
+    int handled = 0;
+    if ((rc = plane_backward(d, dptr<float>(rois), lv, dptr<float>(grad_out), R, pooled_h, pooled_w, sample_ratio,
+                             finest_scale, accumulate, workspace, workspace_bytes, st, &handled))) return rc;
+    if (handled) return MXD_OK;
+  }
   if (!accumulate)
-    for (int l = 0; l < num_levels; ++l) {
+    for (int l = 0; l < num_levels; ++l)
       MXD_CUDA_OK(cudaMemsetAsync(d.feat[l], 0, sizeof(float) * (size_t)numel(grad_feats[l]), st));
-      count_launch();
-    }
-  return launch_gather<true>(d, dptr<float>(rois), levels ? dptr<int>(levels) : nullptr,
-                             dptr<float>(grad_out), R, pooled_h, pooled_w, sample_ratio, finest_scale, st);
+  return launch_gather<true>(d, dptr<float>(rois), lv, dptr<float>(grad_out), R, pooled_h, pooled_w, sample_ratio,
+                             finest_scale, st);
 }
 
 int mxd_roi_align_forward(const DLTensor* data, const DLTensor* rois, DLTensor* out, int pooled_h,
-                          int pooled_w, float spatial_scale, int sample_ratio, void* stream) {
+                          int pooled_w, float spatial_scale, int sample_ratio, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   return mxd_roi_align_fpn_forward(&data, 1, &spatial_scale, rois, nullptr, out, pooled_h, pooled_w,
-                                   sample_ratio, 56.0f, stream);
+                                   sample_ratio, 56.0f, workspace, workspace_bytes, stream);
 }
 
 int mxd_roi_align_backward(const DLTensor* grad_out, const DLTensor* rois, DLTensor* grad_data,
                            int pooled_h, int pooled_w, float spatial_scale, int sample_ratio,
-                           int accumulate, void* stream) {
+                           int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
   return mxd_roi_align_fpn_backward(grad_out, rois, nullptr, &grad_data, 1, &spatial_scale, pooled_h,
-                                    pooled_w, sample_ratio, 56.0f, accumulate, stream);
+                                    pooled_w, sample_ratio, 56.0f, accumulate, workspace, workspace_bytes, stream);
 }
 
 int mxd_map_roi_levels(const DLTensor* rois, DLTensor* levels, int num_levels, float finest_scale,

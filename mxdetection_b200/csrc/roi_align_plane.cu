@@ -1,0 +1,698 @@
+// Plane-resident RoIAlign forward / backward for B200 (Spec A, G).
+//
+// Contract as roi_align.cu (mx.nd.contrib.ROIAlign, mxdetection/ops,
+// /root/reference/README.md:24; SingleLevelRoI.forward,
+// /root/reference/README.md:32).  Design:
+//
+//  * NCHW makes one channel plane a contiguous byte range, so a band of rows of a
+//    plane is ONE cp.async.bulk (TMA, UBLKCP) into shared memory, completion
+//    signalled on an mbarrier; no register staging, no LSU instructions.
+//  * A planner kernel (one warp per RoI) evaluates Spec A's per-axis sample
+//    tables once per RoI (they are shared by all C channels), assigns the RoI to
+//    the row band holding its first tap row and packs the tables to 8 B / entry.
+//  * A persistent kernel (one or two CTAs per SM, work-stealing over an atomic
+//    counter) walks items (image, level, band, channel group): it lands the band
+//    in shared memory, then every thread produces outputs (RoI, bin) of that band
+//    with 16 shared-memory taps per output; each plane byte crosses L2->SM once
+//    per band instead of once per RoI, and never leaves L2 twice.
+//  * RoIs that do not fit a band window, sample outside the image or have a bad
+//    batch index are few; the same kernel processes them afterwards with the
+//    generic global-memory gather (gather_roi_chunk).
+#include "roi_align.cuh"
+
+namespace mxd {
+
+typedef unsigned long long u64;
+
+constexpr int kSmemLimit = 227 * 1024;       // per-CTA opt-in maximum on sm_100
+constexpr int kBigRing = 14 * 1024;          // table area in one-CTA-per-SM mode: leaves 54400 floats = a 200x272 plane
+constexpr int kSmallRing = 8 * 1024;
+constexpr int kMiscBytes = 512;              // mbarrier + scalars + staged RoI ids
+
+struct PlanLevel {
+  int H, W;
+  int band_rows;   // anchor band height (0: level not plane-capable -> gather fallback)
+  int max_rows;    // rows of one window that fit the smem budget
+  int nbands;
+  int cg, ncg;     // channels per item, number of channel groups
+  int band_base;   // first band of this level inside one image's band table
+  int item_base;   // first item id of this level
+  int n_items;     // N * nbands * ncg
+};
+
+struct PlanCfg {
+  PlanLevel lv[MXD_MAX_LEVELS];
+  int L, N, C, PH, PW, sr, ty, tx;
+  int bands_per_img, NB, n_plane_items;
+  int budget_floats, chunk_rois, tab_bytes, slot_bytes;
+  int threads, smem_bytes, ctas_per_sm, group;
+  float finest;
+};
+
+struct PlanWs {
+  int* hdr;      // [0] work counter, [1] fallback count
+  int* cnt;      // [NB] RoIs per band
+  int* rmax;     // [NB] last tap row over the band's RoIs
+  int* start;    // [NB] exclusive prefix of cnt
+  int* cursor;   // [NB]
+  int* meta;     // [R] band index or -1
+  int* list;     // [R] RoI ids grouped by band
+  int* fb_list;  // [R] RoIs for the gather fallback
+  uint2* tab;    // [R][ty+tx] packed {offset | hi_bit<<31, lo-weight bits}
+  size_t bytes;
+};
+
+static PlanWs carve_plan(void* base, int R, int NB, int entries) {
+  PlanWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (char*)base + o; };
+  w.hdr = (int*)take(sizeof(int) * 64);
+  w.cnt = (int*)take(sizeof(int) * (size_t)NB);
+  w.rmax = (int*)take(sizeof(int) * (size_t)NB);
+  w.start = (int*)take(sizeof(int) * (size_t)NB);
+  w.cursor = (int*)take(sizeof(int) * (size_t)NB);
+  w.meta = (int*)take(sizeof(int) * (size_t)(R > 0 ? R : 1));
+  w.list = (int*)take(sizeof(int) * (size_t)(R > 0 ? R : 1));
+  w.fb_list = (int*)take(sizeof(int) * (size_t)(R > 0 ? R : 1));
+  w.tab = (uint2*)take(sizeof(uint2) * (size_t)(R > 0 ? R : 1) * entries);
+  w.bytes = off;
+  return w;
+}
+
+// Host: choose bands / channel groups per level for the shared-memory budget.
+static bool make_cfg(int N, int C, int L, const int* Hs, const int* Ws, int PH, int PW, int sr, float finest,
+                     PlanCfg* c) {
+  if (sr <= 0 || PH * sr > 64 || PW * sr > 32) return false;   // adaptive / very fine sampling: gather kernels
+  memset(c, 0, sizeof(*c));
+  c->L = L; c->N = N; c->C = C; c->PH = PH; c->PW = PW; c->sr = sr; c->ty = PH * sr; c->tx = PW * sr;
+  c->finest = finest;
+  const int entry_bytes = (c->ty + c->tx) * (int)sizeof(uint2);
+  // "big" mode: one CTA per SM with (almost) all shared memory, when some plane fits only that way
+  const int small_est = (kSmemLimit / 2 - 1024 - kSmallRing - kMiscBytes) / 4;
+  const int big_est = (kSmemLimit - kBigRing - kMiscBytes) / 4;
+  bool big = false;
+  for (int l = 0; l < L; ++l) {
+    const size_t plane = (size_t)Hs[l] * Ws[l];
+    if (plane > (size_t)small_est && plane <= (size_t)big_est) big = true;
+  }
+  // planes that fit neither way are banded; banding prefers two CTAs per SM
+  for (int l = 0; l < L; ++l)
+    if ((size_t)Hs[l] * Ws[l] > (size_t)big_est) big = false;
+  // one (RoI, channel) job per lane group (16 lanes when PW*sr <= 16, else a warp)
+  c->group = (c->tx <= 16) ? 16 : 32;
+  c->ctas_per_sm = big ? 1 : 2;
+  const int consumers = big ? 992 : 480;           // + one producer warp
+  c->threads = consumers + 32;
+  // every lane group owns one private slot for the packed tap table of its current RoI
+  const int smem_cta = big ? kSmemLimit : (kSmemLimit / 2 - 1024);
+  c->chunk_rois = consumers / c->group;
+  c->tab_bytes = (int)align_up((size_t)c->chunk_rois * entry_bytes, 128);
+  c->slot_bytes = entry_bytes;
+  if (2 * c->group < c->ty + c->tx) return false;   // a lane moves at most two table entries
+  c->budget_floats = ((smem_cta - c->tab_bytes - kMiscBytes) / 4) & ~3;
+  if (c->budget_floats < 4096) return false;
+  c->smem_bytes = c->budget_floats * 4 + c->tab_bytes + kMiscBytes;
+  int band_base = 0, item_base = 0;
+  for (int l = 0; l < L; ++l) {
+    PlanLevel& v = c->lv[l];
+    v.H = Hs[l]; v.W = Ws[l];
+    const int fit_rows = c->budget_floats / v.W;
+    if (fit_rows >= v.H) {                       // whole plane(s) resident
+      v.max_rows = v.H; v.band_rows = v.H; v.nbands = 1;
+      v.cg = c->budget_floats / (v.H * v.W);
+      if (v.cg > C) v.cg = C;
+      if (v.cg > 32) v.cg = 32;
+    } else if (fit_rows >= 16) {                 // row bands: anchor bands of ~60 % of the window
+      v.max_rows = fit_rows;
+      v.band_rows = (fit_rows * 3) / 5;
+      v.nbands = (v.H + v.band_rows - 1) / v.band_rows;
+      v.cg = 1;
+    } else {                                      // rows too wide for a useful window
+      v.max_rows = 0; v.band_rows = 0; v.nbands = 0; v.cg = 1;
+    }
+    v.ncg = (C + v.cg - 1) / v.cg;
+    v.band_base = band_base; band_base += v.nbands;
+    v.item_base = item_base; v.n_items = N * v.nbands * v.ncg; item_base += v.n_items;
+  }
+  c->bands_per_img = band_base;
+  c->NB = N * band_base;
+  c->n_plane_items = item_base;
+  return c->NB > 0;
+}
+
+// ------------------------------------------------------------------- planner ------
+__global__ void __launch_bounds__(256) plan_rois_kernel(FpnDesc d, PlanCfg c, PlanWs w,
+                                                         const float* __restrict__ rois,
+                                                         const int* __restrict__ levels, int R, int bwd) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= R) return;
+  const RoiGeom g = roi_geom(d, rois, levels, n, c.PH, c.PW, c.sr, c.finest);
+  const PlanLevel& v = c.lv[g.ok ? g.lvl : 0];
+  bool ok = g.ok && (bwd || v.band_rows > 0) && g.H >= 2 && g.W >= 2;
+  AxisTap ya[2], xa[2];
+  int rfirst = 0x7fffffff, rlast = -1;
+  bool valid = true;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int t = lane + 32 * k;
+    if (t < c.ty) {
+      ya[k] = axis_tap(g.rsh, g.bh, c.sr, t / c.sr, t % c.sr, g.H, 1);
+      valid = valid && ya[k].valid;
+      rfirst = min(rfirst, ya[k].hi == ya[k].lo ? ya[k].lo - 1 : ya[k].lo); rlast = max(rlast, ya[k].hi);
+    }
+    if (t < c.tx) {
+      xa[k] = axis_tap(g.rsw, g.bw, c.sr, t / c.sr, t % c.sr, g.W, 1);
+      valid = valid && xa[k].valid;
+    }
+  }
+  rfirst = __reduce_min_sync(0xffffffffu, rfirst);
+  rlast = __reduce_max_sync(0xffffffffu, rlast);
+  ok = ok && __all_sync(0xffffffffu, valid);
+  int band = 0, r0 = 0;
+  if (ok && !bwd) {
+    band = rfirst / v.band_rows;
+    r0 = band * v.band_rows;
+    if (rlast - r0 + 1 > v.max_rows) ok = false;   // the whole footprint must sit inside one window
+  }
+  if (!ok) {
+    if (lane == 0) {
+      w.meta[n] = -1;
+      if (!bwd) w.fb_list[atomicAdd(&w.hdr[1], 1)] = n;   // backward: the rows kernel checks meta itself
+    }
+    return;
+  }
+  const int bidx = g.b * c.bands_per_img + v.band_base + band;
+  uint2* tab = w.tab + (size_t)n * (c.ty + c.tx);
+  // Entries are stored in "unclamped" form: low tap t, high tap t+1, weight l of the high tap.  A sample
+  // clamped at the border (lo == hi == size-1, l == 0) becomes (size-2, l = 1): h*D[size-2] + l*D[size-1]
+  // = D[size-1], the same value, so the kernel can address the 2x2 patch with fixed +1 / +pitch offsets.
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int t = lane + 32 * k;
+    if (t < c.ty) {
+      const bool cl = ya[k].hi == ya[k].lo;
+      const int lo = cl ? ya[k].lo - 1 : ya[k].lo;
+      // forward: byte offset of the low row inside the window; backward: absolute low row
+      const unsigned off = bwd ? (unsigned)lo : (unsigned)((lo - r0) * v.W * 4);
+      tab[t] = make_uint2(off, __float_as_uint(cl ? 1.0f : ya[k].l));
+    }
+    if (t < c.tx) {
+      const bool cl = xa[k].hi == xa[k].lo;
+      tab[c.ty + t] = make_uint2((unsigned)((cl ? xa[k].lo - 1 : xa[k].lo) * 4), __float_as_uint(cl ? 1.0f : xa[k].l));
+    }
+  }
+  if (lane == 0) {
+    if (!bwd) {
+      w.meta[n] = bidx;
+      atomicAdd(&w.cnt[bidx], 1);
+      atomicMax(&w.rmax[bidx], rlast);
+    } else {
+      w.meta[n] = 0;     // backward: tables only (rows kernel), no band lists
+    }
+  }
+}
+
+// Exclusive scan of the band counts + grouping of the RoI ids (single CTA).
+__global__ void __launch_bounds__(1024) plan_group_kernel(PlanCfg c, PlanWs w, int R, int bwd) {
+  __shared__ int s_part[1024];
+  const int tid = threadIdx.x;
+  const int per = (c.NB + 1023) / 1024;
+  int sum = 0;
+  for (int i = tid * per; i < min(c.NB, (tid + 1) * per); ++i) sum += w.cnt[i];
+  s_part[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    int v = tid >= o ? s_part[tid - o] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int run = s_part[tid] - sum;
+  for (int i = tid * per; i < min(c.NB, (tid + 1) * per); ++i) {
+    w.start[i] = run;
+    run += w.cnt[i];
+  }
+  __syncthreads();
+  __threadfence_block();
+  for (int n = tid; n < R; n += 1024) {
+    const int m = w.meta[n];
+    if (m < 0) continue;
+    w.list[w.start[m] + atomicAdd(&w.cursor[m], 1)] = n;
+  }
+}
+
+// -------------------------------------------------------------- PTX helpers ------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ float ldf(const char* p) { return *reinterpret_cast<const float*>(p); }
+
+struct ItemDesc { int lvl, img, band, cgi; };
+
+__device__ __forceinline__ ItemDesc decode_item(const PlanCfg& c, int item) {
+  ItemDesc it;
+  int l = 0;
+  while (l + 1 < c.L && item >= c.lv[l + 1].item_base) ++l;
+  const PlanLevel& v = c.lv[l];
+  int r = item - v.item_base;
+  it.lvl = l;
+  it.cgi = r % v.ncg; r /= v.ncg;
+  it.band = r % v.nbands;
+  it.img = r / v.nbands;
+  return it;
+}
+
+// --------------------------------------------------------------- forward ---------
+// Shared-memory map of the persistent kernels:
+//   [band buffer: budget_floats*4][per-group tap tables: ngroups*ent*8][SmemCtl]
+struct ItemSlot {
+  int kind;            // 0 plane item, 1 gather fallback unit, 2 stop
+  int lvl, img, c0, ncur, cnt, nrows, bulk;
+  int chan_bytes, pitch_bytes;
+  int lst;             // first entry of the band's RoI list
+  int r0;              // first row of the window
+  int fb_roi, fb_c0;
+};
+struct SmemCtl {
+  u64 desc_full, band_full, band_empty;
+  ItemSlot item;
+};
+
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+// Producer warp of the persistent kernels: pulls items off the global counter, waits until the
+// consumers released the band buffer, publishes the item descriptor and issues the TMA band loads.
+__device__ __forceinline__ void plane_producer(const FpnDesc& d, const PlanCfg& c, const PlanWs& w, SmemCtl* ctl,
+                                               float* buf, int lane, bool load_band) {
+  const int n_fb = w.hdr[1];
+  const int fb_chunks = (c.C + 31) / 32;
+  // the backward runs its fallback RoIs in a second kernel (after the bands are written)
+  const int total = c.n_plane_items + (load_band ? n_fb * fb_chunks : 0);
+  uint32_t band_phase = 0;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(&w.hdr[0], 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    ItemSlot it;
+    it.kind = 2;
+    it.lvl = it.img = it.c0 = it.ncur = it.cnt = it.nrows = it.bulk = it.chan_bytes = it.pitch_bytes = 0;
+    it.lst = it.r0 = it.fb_roi = it.fb_c0 = 0;
+    const float* src0 = nullptr;
+    size_t plane_sz = 0;
+    if (item < c.n_plane_items) {
+      const ItemDesc de = decode_item(c, item);
+      const PlanLevel& v = c.lv[de.lvl];
+      const int bidx = de.img * c.bands_per_img + v.band_base + de.band;
+      const int cnt = w.cnt[bidx];
+      if (cnt == 0 && load_band) continue;   // forward: nothing to pool from this band (warp-uniform)
+      it.r0 = de.band * v.band_rows;
+      it.kind = 0; it.lvl = de.lvl; it.img = de.img; it.cnt = cnt;
+      it.nrows = load_band ? min(w.rmax[bidx], v.H - 1) - it.r0 + 1 : min(v.band_rows, v.H - it.r0);
+      it.c0 = de.cgi * v.cg;
+      it.ncur = min(v.cg, c.C - it.c0);
+      it.pitch_bytes = v.W * 4;
+      it.chan_bytes = it.nrows * v.W * 4;
+      it.bulk = load_band && ((v.W & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.feat[de.lvl]) & 15) == 0);
+      it.lst = w.start[bidx];
+      src0 = d.feat[de.lvl] + (((size_t)de.img * c.C + it.c0) * v.H + it.r0) * v.W;
+      plane_sz = (size_t)v.H * v.W;
+    } else if (item < total) {
+      const int f = item - c.n_plane_items;
+      it.kind = 1; it.fb_roi = w.fb_list[f / fb_chunks]; it.fb_c0 = (f % fb_chunks) * 32;
+    }
+    // the band buffer (and the descriptor) is free once every consumer warp released it
+    mbar_wait(&ctl->band_empty, band_phase ^ 1);
+    if (lane == 0) {
+      ctl->item = it;
+      mbar_arrive(&ctl->desc_full);
+      if (it.kind == 0 && it.bulk) {
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&ctl->band_full, (uint32_t)(it.ncur * it.chan_bytes));
+        for (int j = 0; j < it.ncur; ++j)
+          bulk_g2s(reinterpret_cast<char*>(buf) + (size_t)j * it.chan_bytes, src0 + (size_t)j * plane_sz,
+                   (uint32_t)it.chan_bytes, &ctl->band_full);
+      } else {
+        mbar_arrive(&ctl->band_full);
+      }
+    }
+    band_phase ^= 1;
+    if (it.kind == 2) break;
+  }
+}
+
+template <int SR>
+__global__ void __launch_bounds__(1024, 1)
+roi_align_plane_fwd_kernel(const __grid_constant__ FpnDesc d, const __grid_constant__ PlanCfg c, PlanWs w,
+                           const float* __restrict__ rois, const int* __restrict__ levels,
+                           float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* buf = reinterpret_cast<float*>(smem);
+  uint2* tab_all = reinterpret_cast<uint2*>(smem + (size_t)c.budget_floats * 4);
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + (size_t)c.budget_floats * 4 + c.tab_bytes);
+  const int tid = threadIdx.x;
+  const int Tc = blockDim.x - 32;            // consumer threads; the last warp is the producer
+  const int bins = c.PH * c.PW;
+  const int ent = c.ty + c.tx;
+  const int sr = SR > 0 ? SR : c.sr;
+  const int n_cwarps = Tc >> 5;
+  if (tid == 0) {
+    mbar_init(&ctl->desc_full, 1);
+    mbar_init(&ctl->band_full, 1);
+    mbar_init(&ctl->band_empty, n_cwarps);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid >= Tc) {
+    plane_producer(d, c, w, ctl, buf, tid - Tc, true);
+    return;
+  }
+
+  // ================================= consumer warps ====================================
+  // One (RoI, channel) job per lane group (c.group = 16 or 32 lanes).  Lane gl owns x-sample gl:
+  // consecutive lanes read increasing x of one feature row (bank-conflict free); the 2x2 patch of a
+  // sample sits at [R], [R+4], [R+pitch], [R+pitch+4] with R = plane + x_off + y_off; the sr x-samples of
+  // a bin are summed with shuffles and the lane of the first one stores the bin.  Each group keeps its
+  // RoI's packed tap table in a private shared-memory slot, prefetched through registers one RoI ahead
+  // (ids two ahead) so no global latency sits between jobs.
+  const int grp = tid / c.group, gl = tid % c.group, ngroups = Tc / c.group;
+  uint2* te = tab_all + (size_t)grp * ent;
+  const float inv_count = 1.0f / (float)(sr * sr);
+  const bool warp_lead = (tid & 31) == 0;
+  const int e0 = gl, e1 = gl + c.group;      // table entries this lane moves (ent <= 2*group)
+  uint32_t phase = 0;
+  for (;;) {
+    mbar_wait(&ctl->desc_full, phase);
+    const ItemSlot it = ctl->item;
+    if (it.kind == 2) break;
+    if (it.kind == 1) {
+      mbar_wait(&ctl->band_full, phase);
+      phase ^= 1;
+      const RoiGeom g = roi_geom(d, rois, levels, it.fb_roi, c.PH, c.PW, c.sr, c.finest);
+      gather_roi_chunk<false>(d, g, it.fb_roi, it.fb_c0, min(32, c.C - it.fb_c0), out, c.PH, c.PW, tid, Tc);
+      __syncwarp();
+      if (warp_lead) mbar_arrive(&ctl->band_empty);
+      continue;
+    }
+    // prefetch ids / first table while the band is in flight
+    const int* list = w.list + it.lst;
+    int id0 = grp < it.cnt ? list[grp] : -1;
+    int id1 = grp + ngroups < it.cnt ? list[grp + ngroups] : -1;
+    uint2 t0 = make_uint2(0, 0), t1 = make_uint2(0, 0);
+    if (id0 >= 0) {
+      if (e0 < ent) t0 = w.tab[(size_t)id0 * ent + e0];
+      if (e1 < ent) t1 = w.tab[(size_t)id0 * ent + e1];
+    }
+    mbar_wait(&ctl->band_full, phase);
+    phase ^= 1;
+    if (!it.bulk) {   // rows not 16-byte aligned: cooperative load by the consumers
+      const PlanLevel& v = c.lv[it.lvl];
+      const int chan_floats = it.chan_bytes >> 2;
+      const float* src0 = d.feat[it.lvl] + (((size_t)it.img * c.C + it.c0) * v.H + it.r0) * v.W;
+      for (int i = tid; i < it.ncur * chan_floats; i += Tc) {
+        const int j = i / chan_floats;
+        buf[i] = __ldg(src0 + (size_t)j * v.H * v.W + (i - j * chan_floats));
+      }
+      consumer_sync(Tc);
+    }
+    const int pitch_bytes = it.pitch_bytes;
+    const int rounds = (it.cnt + ngroups - 1) / ngroups;
+    for (int k = 0; k < rounds; ++k) {
+      const int n = id0;
+      const bool live = n >= 0;
+      __syncwarp();                       // previous job's reads of the slot are done
+      if (e0 < ent) te[e0] = t0;
+      if (e1 < ent) te[e1] = t1;
+      __syncwarp();
+      {   // prefetch: id two jobs ahead, table one job ahead
+        const int q2 = grp + (k + 2) * ngroups;
+        const int id2 = q2 < it.cnt ? list[q2] : -1;
+        if (id1 >= 0) {
+          if (e0 < ent) t0 = w.tab[(size_t)id1 * ent + e0];
+          if (e1 < ent) t1 = w.tab[(size_t)id1 * ent + e1];
+        }
+        id0 = id1; id1 = id2;
+      }
+      const bool lane_on = live && gl < c.tx;
+      const uint2 ex = te[c.ty + (gl < c.tx ? gl : 0)];
+      const float lx = __uint_as_float(ex.y), hx = 1.0f - lx;
+      const bool writer = lane_on && (gl % sr == 0);
+      for (int j = 0; j < it.ncur; ++j) {
+        const char* px = reinterpret_cast<const char*>(buf) + (size_t)j * it.chan_bytes + (live ? ex.x : 0);
+        float* o = out + ((size_t)(live ? n : 0) * c.C + it.c0 + j) * bins + gl / sr;
+        for (int ph = 0; ph < c.PH; ++ph) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int iy = 0; iy < (SR > 0 ? SR : 1); ++iy) {
+            const uint2 ey = te[ph * sr + iy];
+            const char* r = px + (live ? ey.x : 0);
+            const float ly = __uint_as_float(ey.y), hy = 1.0f - ly;
+            const float a = hx * ldf(r) + lx * ldf(r + 4);
+            const float b = hx * ldf(r + pitch_bytes) + lx * ldf(r + pitch_bytes + 4);
+            acc += hy * a + ly * b;
+          }
+          if (SR == 0) {   // runtime sample ratio: remaining rows
+            for (int iy = 1; iy < sr; ++iy) {
+              const uint2 ey = te[ph * sr + iy];
+              const char* r = px + (live ? ey.x : 0);
+              const float ly = __uint_as_float(ey.y), hy = 1.0f - ly;
+              const float a = hx * ldf(r) + lx * ldf(r + 4);
+              const float b = hx * ldf(r + pitch_bytes) + lx * ldf(r + pitch_bytes + 4);
+              acc += hy * a + ly * b;
+            }
+          }
+          float sum;
+          if (SR == 2) {
+            sum = acc + __shfl_xor_sync(0xffffffffu, acc, 1);
+          } else {
+            const int base = (threadIdx.x & 31) - gl % sr;
+            sum = 0.0f;
+            for (int kk = 0; kk < sr; ++kk) sum += __shfl_sync(0xffffffffu, acc, base + kk);
+          }
+          if (writer) o[ph * c.PW] = sum * inv_count;
+        }
+      }
+    }
+    __syncwarp();
+    if (warp_lead) mbar_arrive(&ctl->band_empty);
+  }
+}
+
+// --------------------------------------------------------------- backward --------
+// L2 RED.ADD throughput on B200 is bound per 32-byte SECTOR touched by a warp-level RED instruction
+// (~200 G sector-ops/s, profiles/microbench), not per lane, and shared-memory fp32 atomics are CAS
+// loops that are no faster (a band-resident CAS variant measured 1.87 ms on BASELINE config 3 against
+// 1.80 ms for per-tap REDs).  So the backward minimises sector-ops instead:
+//   * lane gl of a 16/32-lane group owns x-sample gl of one (RoI, channel): the lanes of one RED
+//     instruction hit a few adjacent sectors of ONE gradient row;
+//   * the high tap of lane gl and the low tap of lane gl+1 usually fall on the same column: it is handed
+//     over with one shuffle and added once;
+//   * the high row of sample row sy and the low row of sy+1 usually coincide: it is carried in
+//     registers and written once.
+// Both merges are optimisations only - every write is still an atomic RED, so overlapping RoIs,
+// coincident samples and clamped borders stay exact.  One CTA per (RoI, 32-channel chunk).
+constexpr int kRowsBwdThreads = 256;
+
+template <int SR>
+__global__ void __launch_bounds__(kRowsBwdThreads)
+roi_align_rows_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_constant__ PlanCfg c, PlanWs w,
+                          const float* __restrict__ rois, const int* __restrict__ levels,
+                          float* __restrict__ gout, int cchunk) {
+  __shared__ uint2 te[128];
+  const int n = blockIdx.x;
+  const int c0 = blockIdx.y * cchunk;
+  const int cc = min(cchunk, c.C - c0);
+  const int tid = threadIdx.x;
+  const RoiGeom g = roi_geom(d, rois, levels, n, c.PH, c.PW, c.sr, c.finest);
+  if (w.meta[n] < 0) {   // bad index / samples outside the image: generic per-tap path
+    gather_roi_chunk<true>(d, g, n, c0, cc, gout, c.PH, c.PW, tid, kRowsBwdThreads);
+    return;
+  }
+  const int ent = c.ty + c.tx;
+  const int sr = SR > 0 ? SR : c.sr;
+  const int bins = c.PH * c.PW;
+  for (int t = tid; t < ent; t += kRowsBwdThreads) te[t] = w.tab[(size_t)n * ent + t];
+  __syncthreads();
+  const int grp = tid / c.group, gl = tid % c.group, ngroups = kRowsBwdThreads / c.group;
+  const bool lane_on = gl < c.tx;
+  const uint2 ex = te[c.ty + (lane_on ? gl : 0)];
+  const int xo = (int)(ex.x >> 2);
+  const float lx = __uint_as_float(ex.y), hx = 1.0f - lx;
+  // column hand-over between neighbouring lanes of the group
+  const int xo_prev = __shfl_up_sync(0xffffffffu, xo, 1), xo_next = __shfl_down_sync(0xffffffffu, xo, 1);
+  const bool take_prev = lane_on && gl > 0 && xo == xo_prev + 1;
+  const bool give_next = lane_on && gl + 1 < c.tx && xo_next == xo + 1;
+  const float inv_count = 1.0f / (float)(sr * sr);
+  const int W = g.W;
+  const size_t plane_sz = (size_t)g.H * W;
+  const int rounds = (cc + ngroups - 1) / ngroups;
+  for (int k = 0; k < rounds; ++k) {
+    const int cj = k * ngroups + grp;
+    const bool live = cj < cc && lane_on;
+    float* plane = g.plane0 + (size_t)(c0 + (cj < cc ? cj : 0)) * plane_sz + xo;
+    const float* gj = gout + ((size_t)n * c.C + c0 + (cj < cc ? cj : 0)) * bins + (lane_on ? gl / sr : 0);
+    float carry_lo = 0.0f, carry_hi = 0.0f;
+    int carry_row = -1;
+    // one merged row write: hand the high tap to the next lane when it owns that column
+    auto flush = [&](int row, float lo, float hi) {
+      const float recv = __shfl_up_sync(0xffffffffu, hi, 1);
+      if (take_prev) lo += recv;
+      if (live) {
+        float* r = plane + (size_t)row * W;
+        atomicAdd(r, lo);
+        if (!give_next) atomicAdd(r + 1, hi);
+      }
+    };
+    float g_next = __ldg(gj);
+    for (int ph = 0; ph < c.PH; ++ph) {
+      const float gv = g_next * inv_count;
+      if (ph + 1 < c.PH) g_next = __ldg(gj + (ph + 1) * c.PW);
+      const float ghx = gv * hx, glx = gv * lx;
+#pragma unroll
+      for (int iy = 0; iy < (SR > 0 ? SR : 1); ++iy) {
+        const uint2 ey = te[ph * sr + iy];
+        const int row = (int)ey.x;
+        const float ly = __uint_as_float(ey.y), hy = 1.0f - ly;
+        float a_lo = ghx * hy, a_hi = glx * hy;
+        if (row == carry_row) {          // group-uniform: the carried high row is this low row
+          a_lo += carry_lo; a_hi += carry_hi;
+        } else if (carry_row >= 0) {
+          flush(carry_row, carry_lo, carry_hi);
+        }
+        flush(row, a_lo, a_hi);
+        carry_row = row + 1; carry_lo = ghx * ly; carry_hi = glx * ly;
+      }
+      if (SR == 0) {
+        for (int iy = 1; iy < sr; ++iy) {
+          const uint2 ey = te[ph * sr + iy];
+          const int row = (int)ey.x;
+          const float ly = __uint_as_float(ey.y), hy = 1.0f - ly;
+          float a_lo = ghx * hy, a_hi = glx * hy;
+          if (row == carry_row) {
+            a_lo += carry_lo; a_hi += carry_hi;
+          } else if (carry_row >= 0) {
+            flush(carry_row, carry_lo, carry_hi);
+          }
+          flush(row, a_lo, a_hi);
+          carry_row = row + 1; carry_lo = ghx * ly; carry_hi = glx * ly;
+        }
+      }
+    }
+    if (carry_row >= 0) flush(carry_row, carry_lo, carry_hi);
+  }
+}
+
+}  // namespace mxd
+
+namespace mxd {
+
+size_t plane_workspace_bytes(int R, int N, int L, const int* Hs, const int* Ws, int C, int PH, int PW, int sr) {
+  PlanCfg c;
+  if (!make_cfg(N, C, L, Hs, Ws, PH, PW, sr, 56.0f, &c)) return 256;
+  return carve_plan(nullptr, R, c.NB, c.ty + c.tx).bytes;
+}
+
+static int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+static int run_planner(const FpnDesc& d, const PlanCfg& c, const PlanWs& w, const float* rois, const int* levels,
+                       int R, int bwd, cudaStream_t st) {
+  // zero hdr, cnt, rmax, start, cursor in one go (they are contiguous)
+  const size_t zbytes = (size_t)((char*)w.meta - (char*)w.hdr);
+  MXD_CUDA_OK(cudaMemsetAsync(w.hdr, 0, zbytes, st));
+  if (R == 0) return MXD_OK;
+  plan_rois_kernel<<<(R * 32 + 255) / 256, 256, 0, st>>>(d, c, w, rois, levels, R, bwd);
+  MXD_POST_LAUNCH("roi_align_plan_rois");
+  plan_group_kernel<<<1, 1024, 0, st>>>(c, w, R, bwd);
+  MXD_POST_LAUNCH("roi_align_plan_group");
+  return MXD_OK;
+}
+
+int plane_forward(const FpnDesc& d, const float* rois, const int* levels, float* out, int R, int PH, int PW, int sr,
+                  float finest, void* ws, size_t ws_bytes, cudaStream_t st, int* handled) {
+  *handled = 0;
+  PlanCfg c;
+  if (R == 0 || d.C == 0) return MXD_OK;
+  if (!make_cfg(d.N, d.C, d.num_levels, d.H, d.W, PH, PW, sr, finest, &c)) return MXD_OK;
+  PlanWs w = carve_plan(ws, R, c.NB, c.ty + c.tx);
+  MXD_REQUIRE(ws_bytes >= w.bytes, MXD_EWORKSPACE, "roi_align workspace %zu < %zu bytes", ws_bytes, w.bytes);
+  MXD_REQUIRE(((uintptr_t)ws & 255) == 0, MXD_EINVAL, "workspace must be 256-byte aligned");
+  int rc;
+  if ((rc = run_planner(d, c, w, rois, levels, R, 0, st))) return rc;
+  auto kern = (sr == 2) ? roi_align_plane_fwd_kernel<2> : roi_align_plane_fwd_kernel<0>;
+  static int attr_done[2] = {0, 0};
+  const int ki = sr == 2 ? 0 : 1;
+  if (attr_done[ki] < c.smem_bytes) {
+    MXD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_done[ki] = kSmemLimit;
+  }
+  kern<<<num_sms() * c.ctas_per_sm, c.threads, c.smem_bytes, st>>>(d, c, w, rois, levels, out);
+  MXD_POST_LAUNCH("roi_align_plane_fwd");
+  *handled = 1;
+  return MXD_OK;
+}
+
+int plane_backward(const FpnDesc& d, const float* rois, const int* levels, const float* gout, int R, int PH, int PW,
+                   int sr, float finest, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st, int* handled) {
+  *handled = 0;
+  PlanCfg c;
+  if (R == 0 || d.C == 0) return MXD_OK;
+  if (!make_cfg(d.N, d.C, d.num_levels, d.H, d.W, PH, PW, sr, finest, &c)) return MXD_OK;
+  PlanWs w = carve_plan(ws, R, c.NB, c.ty + c.tx);
+  MXD_REQUIRE(ws_bytes >= w.bytes, MXD_EWORKSPACE, "roi_align workspace %zu < %zu bytes", ws_bytes, w.bytes);
+  MXD_REQUIRE(((uintptr_t)ws & 255) == 0, MXD_EINVAL, "workspace must be 256-byte aligned");
+  if (!accumulate)
+    for (int l = 0; l < c.L; ++l)
+      MXD_CUDA_OK(cudaMemsetAsync(d.feat[l], 0, sizeof(float) * (size_t)d.N * d.C * d.H[l] * d.W[l], st));
+  plan_rois_kernel<<<(R * 32 + 255) / 256, 256, 0, st>>>(d, c, w, rois, levels, R, 1);
+  MXD_POST_LAUNCH("roi_align_plan_rois");
+  const int ngroups = kRowsBwdThreads / c.group;
+  int cchunk = 2 * ngroups;                       // two channels per lane group per CTA
+  while ((d.C + cchunk - 1) / cchunk > 65535) cchunk *= 2;
+  dim3 grid(R, (d.C + cchunk - 1) / cchunk);
+  if (sr == 2)
+    roi_align_rows_bwd_kernel<2><<<grid, kRowsBwdThreads, 0, st>>>(d, c, w, rois, levels, const_cast<float*>(gout), cchunk);
+  else
+    roi_align_rows_bwd_kernel<0><<<grid, kRowsBwdThreads, 0, st>>>(d, c, w, rois, levels, const_cast<float*>(gout), cchunk);
+  MXD_POST_LAUNCH("roi_align_rows_bwd");
+  *handled = 1;
+  return MXD_OK;
+}
+
+}  // namespace mxd

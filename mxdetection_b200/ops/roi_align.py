@@ -17,6 +17,22 @@ def _pair(v):
     return (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
 
 
+USE_PLANE_KERNELS = True   # False: pass workspace=NULL so the library uses its gather kernels (A/B testing)
+
+
+def _ws(num_rois, shapes, ph, pw, sample_ratio, device):
+    """Scratch for the plane-resident kernels (RoI plan + packed tap tables)."""
+    if not USE_PLANE_KERNELS:
+        return None, 0
+    n_lv = len(shapes)
+    hs = (ctypes.c_int * n_lv)(*[int(s[2]) for s in shapes])
+    ws_ = (ctypes.c_int * n_lv)(*[int(s[3]) for s in shapes])
+    nbytes = L.lib.mxd_roi_align_workspace_bytes(int(num_rois), int(shapes[0][0]), int(shapes[0][1]), n_lv, hs, ws_,
+                                                 ph, pw, int(sample_ratio))
+    buf = L.workspace(nbytes, device, "roi_align")
+    return buf.data_ptr(), buf.numel()
+
+
 def roi_align_forward(data, rois, pooled_size, spatial_scale, sample_ratio=-1, out=None):
     """data (N,C,H,W) f32 cuda, rois (R,5) [batch,x1,y1,x2,y2] -> (R,C,PH,PW)."""
     L.require_cuda(data, rois)
@@ -24,21 +40,25 @@ def roi_align_forward(data, rois, pooled_size, spatial_scale, sample_ratio=-1, o
     data = data.contiguous(); rois = rois.contiguous()
     if out is None:
         out = torch.empty((rois.shape[0], data.shape[1], ph, pw), dtype=torch.float32, device=data.device)
+    wp, wn = _ws(rois.shape[0], [data.shape], ph, pw, sample_ratio, data.device)
     L.call("mxd_roi_align_forward", L.dl(data), L.dl(rois), L.dl(out), ph, pw, float(spatial_scale),
-           int(sample_ratio), L.current_stream(data.device))
+           int(sample_ratio), wp, wn, L.current_stream(data.device))
     return out
 
 
-def roi_align_backward(grad_out, rois, data_shape, pooled_size, spatial_scale, sample_ratio=-1, grad_data=None):
-    """Returns grad wrt data.  grad_data given => req='add' (accumulated in place)."""
+def roi_align_backward(grad_out, rois, data_shape, pooled_size, spatial_scale, sample_ratio=-1, grad_data=None,
+                       accumulate=False):
+    """Returns grad wrt data.  grad_data: optional destination; accumulate=True is req='add'
+    (added in place), False is req='write' (the library zero-fills it first)."""
     L.require_cuda(grad_out, rois)
     ph, pw = _pair(pooled_size)
     grad_out = grad_out.contiguous(); rois = rois.contiguous()
-    accumulate = grad_data is not None
     if grad_data is None:
+        accumulate = False
         grad_data = torch.empty(tuple(data_shape), dtype=torch.float32, device=grad_out.device)
+    wp, wn = _ws(rois.shape[0], [grad_data.shape], ph, pw, sample_ratio, grad_out.device)
     L.call("mxd_roi_align_backward", L.dl(grad_out), L.dl(rois), L.dl(grad_data), ph, pw, float(spatial_scale),
-           int(sample_ratio), 1 if accumulate else 0, L.current_stream(grad_out.device))
+           int(sample_ratio), 1 if accumulate else 0, wp, wn, L.current_stream(grad_out.device))
     return grad_data
 
 
@@ -56,24 +76,27 @@ def roi_align_fpn_forward(feats, rois, pooled_size, spatial_scales, sample_ratio
     if out is None:
         out = torch.empty((rois.shape[0], feats[0].shape[1], ph, pw), dtype=torch.float32, device=rois.device)
     arr, keep = L.dl_array(feats)
+    wp, wn = _ws(rois.shape[0], [f.shape for f in feats], ph, pw, sample_ratio, rois.device)
     L.call("mxd_roi_align_fpn_forward", arr, len(feats), _scales(spatial_scales), L.dl(rois), L.dl(levels),
-           L.dl(out), ph, pw, int(sample_ratio), float(finest_scale), L.current_stream(rois.device))
+           L.dl(out), ph, pw, int(sample_ratio), float(finest_scale), wp, wn, L.current_stream(rois.device))
     del keep
     return out
 
 
 def roi_align_fpn_backward(grad_out, rois, feat_shapes, pooled_size, spatial_scales, sample_ratio=2, levels=None,
-                           finest_scale=56, grad_feats=None):
+                           finest_scale=56, grad_feats=None, accumulate=False):
+    """grad_feats: optional destinations; accumulate=True adds into them (req='add')."""
     L.require_cuda(grad_out, rois)
     ph, pw = _pair(pooled_size)
     grad_out = grad_out.contiguous(); rois = rois.contiguous()
-    accumulate = grad_feats is not None
     if grad_feats is None:
+        accumulate = False
         grad_feats = [torch.empty(tuple(s), dtype=torch.float32, device=grad_out.device) for s in feat_shapes]
     arr, keep = L.dl_array(grad_feats)
+    wp, wn = _ws(rois.shape[0], [g.shape for g in grad_feats], ph, pw, sample_ratio, rois.device)
     L.call("mxd_roi_align_fpn_backward", L.dl(grad_out), L.dl(rois), L.dl(levels), arr, len(grad_feats),
            _scales(spatial_scales), ph, pw, int(sample_ratio), float(finest_scale), 1 if accumulate else 0,
-           L.current_stream(rois.device))
+           wp, wn, L.current_stream(rois.device))
     del keep
     return grad_feats
 

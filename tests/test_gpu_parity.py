@@ -57,8 +57,18 @@ def test_roi_align_golden(golden_dir, name):
     assert close(gin, g["grad_in"], 1e-4)
 
 
+@pytest.fixture(params=["plane", "gather"])
+def roi_path(request):
+    """Both RoIAlign code paths of the library: plane-resident (workspace given) and gather (workspace NULL)."""
+    import mxdetection_b200.ops.roi_align as ra
+    old = ra.USE_PLANE_KERNELS
+    ra.USE_PLANE_KERNELS = request.param == "plane"
+    yield request.param
+    ra.USE_PLANE_KERNELS = old
+
+
 @pytest.mark.parametrize("sr,ps", [(2, (7, 7)), (2, (14, 14)), (-1, (7, 7)), (4, (7, 7)), (9, (8, 8)), (1, (1, 1))])
-def test_roi_align_vs_oracle_random(sr, ps):
+def test_roi_align_vs_oracle_random(sr, ps, roi_path):
     from mxdetection_b200.ops import roi_align_forward, roi_align_backward
     rng = np.random.default_rng(7 + sr + ps[0])
     Nn, C, H, W = 2, 37, 50, 68           # C not a multiple of the channel chunk
@@ -77,11 +87,11 @@ def test_roi_align_vs_oracle_random(sr, ps):
     # req='add'
     base = rng.standard_normal(data.shape).astype(F)
     acc = T(base.copy())
-    roi_align_backward(T(gout), T(rois), data.shape, ps, 0.25, sr, grad_data=acc)
+    roi_align_backward(T(gout), T(rois), data.shape, ps, 0.25, sr, grad_data=acc, accumulate=True)
     assert close(N(acc), base + gref, 1e-4)
 
 
-def test_roi_align_edge_cases():
+def test_roi_align_edge_cases(roi_path):
     from mxdetection_b200.ops import roi_align_forward, roi_align_backward
     data = np.random.default_rng(0).standard_normal((2, 3, 10, 12)).astype(F)
     rois = np.array([[-1, 0, 0, 10, 10], [0, -500, -500, -400, -400], [1, 44, 36, 47.9, 39.9], [0, 5, 5, 5, 5],
@@ -156,7 +166,7 @@ def test_fpn_roi_extractor_small_and_autograd():
         assert close(N(f.grad), g, 1e-4)
 
 
-def test_fpn_roi_stage_cfg3_shard_full_size():
+def test_fpn_roi_stage_cfg3_shard_full_size(roi_path):
     """BASELINE config 3 geometry (800x1344, 4 levels, 256 ch, 512 RoIs/img), 2 images of the 8."""
     from mxdetection_b200.ops import roi_align_fpn_forward, roi_align_fpn_backward
     d = syn.cfg3(batch=2)
