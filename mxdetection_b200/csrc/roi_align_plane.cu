@@ -541,6 +541,77 @@ roi_align_rows_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
   const int bins = c.PH * c.PW;
   for (int t = tid; t < ent; t += kRowsBwdThreads) te[t] = w.tab[(size_t)n * ent + t];
   __syncthreads();
+  // ---- dense-column mode -------------------------------------------------------------------------
+  // When the RoI's footprint is at most 32 columns wide and every column is fed by samples of at most
+  // two neighbouring bins (bin width >= 1 px), lane i of a group owns footprint column xmin+i: the
+  // x-direction of the adjoint collapses to  e[ph][col] = (A_col*g[ph][p0_col] + B_col*g[ph][p0_col+1])/count
+  // with per-column constants computed once per CTA, and every gradient row is ONE contiguous RED per
+  // group - the minimum number of L2 sectors.  Other RoIs (tiny or very wide) use the per-sample path below.
+  {
+    const int xmin = (int)(te[c.ty].x >> 2);
+    const int Wf = (int)(te[c.ty + c.tx - 1].x >> 2) + 2 - xmin;
+    const int gsz = Wf <= 16 ? 16 : 32;
+    const int col = tid % gsz;
+    float A = 0.0f, B = 0.0f;
+    int p0 = -1, pmax = -1;
+    if (Wf <= 32 && col < Wf) {
+      for (int sx = 0; sx < c.tx; ++sx) {
+        const uint2 e = te[c.ty + sx];
+        const int xs = (int)(e.x >> 2) - xmin;
+        const float l = __uint_as_float(e.y);
+        float wgt = 0.0f;
+        bool hit = false;
+        if (xs == col) { wgt = 1.0f - l; hit = true; }
+        if (xs + 1 == col) { wgt = l; hit = true; }
+        if (hit) {
+          const int pb = sx / sr;
+          if (p0 < 0) p0 = pb;
+          if (pb == p0) A += wgt; else B += wgt;
+          pmax = pb;
+        }
+      }
+    }
+    const int bad = (Wf > 32) || (p0 >= 0 && pmax > p0 + 1);
+    if (!__syncthreads_or(bad)) {
+      const int grp = tid / gsz, ngroups = kRowsBwdThreads / gsz;
+      const bool lane_on = col < Wf && p0 >= 0;
+      const float inv_count = 1.0f / (float)(sr * sr);
+      const int W = g.W;
+      const size_t plane_sz = (size_t)g.H * W;
+      const bool has_b = lane_on && (p0 + 1 < c.PW) && B != 0.0f;
+      const float a_s = A * inv_count, b_s = B * inv_count;
+      for (int cj = grp; cj < cc; cj += ngroups) {
+        float* plane = g.plane0 + (size_t)(c0 + cj) * plane_sz + xmin + col;
+        const float* gj = gout + ((size_t)n * c.C + c0 + cj) * bins + (lane_on ? p0 : 0);
+        float carry = 0.0f;
+        int carry_row = -1;
+        for (int ph = 0; ph < c.PH; ++ph) {
+          float e = 0.0f;
+          if (lane_on) {
+            e = a_s * __ldg(gj + ph * c.PW);
+            if (has_b) e += b_s * __ldg(gj + ph * c.PW + 1);
+          }
+          for (int iy = 0; iy < sr; ++iy) {
+            const uint2 ey = te[ph * sr + iy];
+            const int row = (int)ey.x;
+            const float ly = __uint_as_float(ey.y), hy = 1.0f - ly;
+            float a = e * hy;
+            if (row == carry_row) {
+              a += carry;
+            } else if (carry_row >= 0 && lane_on) {
+              atomicAdd(plane + (size_t)carry_row * W, carry);
+            }
+            if (lane_on) atomicAdd(plane + (size_t)row * W, a);
+            carry_row = row + 1;
+            carry = e * ly;
+          }
+        }
+        if (carry_row >= 0 && lane_on) atomicAdd(plane + (size_t)carry_row * W, carry);
+      }
+      return;
+    }
+  }
+  // ---- per-sample mode ---------------------------------------------------------------------------
   const int grp = tid / c.group, gl = tid % c.group, ngroups = kRowsBwdThreads / c.group;
   const bool lane_on = gl < c.tx;
   const uint2 ex = te[c.ty + (lane_on ? gl : 0)];
