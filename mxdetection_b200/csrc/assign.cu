@@ -69,15 +69,24 @@ __global__ void __launch_bounds__(kAssignThreads) assign_pass1_kernel(AssignArgs
     }
     __syncthreads();
     for (int i = 0; i < gc; ++i) {
+      // Most (anchor, GT) pairs do not intersect: their IoU is +0 without the IEEE division (when the
+      // union is positive), cannot raise gt_max, and the warp skips the REDUX / atomic altogether.
       float iou = 0.0f;
+      bool hit = false;
       if (act) {
-        iou = iou_spec_d(me, area, s_gt[i], s_area[i], a.delta);
+        const float4 g = s_gt[i];
+        const float iw = __fadd_rn(__fsub_rn(fminf(me.z, g.z), fmaxf(me.x, g.x)), a.delta);
+        const float ih = __fadd_rn(__fsub_rn(fminf(me.w, g.w), fmaxf(me.y, g.y)), a.delta);
+        hit = iw > 0.0f && ih > 0.0f;
+        if (hit || !(__fadd_rn(s_area[i], area) > 0.0f)) iou = iou_spec_d(me, area, g, s_area[i], a.delta);
         if (iou > best) { best = iou; arg = g0 + i; }   // strict > keeps the lowest g on ties
       }
-      // NaN / negative IoU (degenerate boxes) never feed gt_max: see DESIGN.md
-      const unsigned bits = (act && iou > 0.0f) ? __float_as_uint(iou) : 0u;
-      const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
-      if (wmax != 0u && (threadIdx.x & 31) == 0) atomicMax(&s_max[i], wmax);
+      if (__any_sync(0xffffffffu, hit)) {
+        // NaN / negative IoU (degenerate boxes) never feed gt_max: see DESIGN.md
+        const unsigned bits = (act && iou > 0.0f) ? __float_as_uint(iou) : 0u;
+        const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
+        if (wmax != 0u && (threadIdx.x & 31) == 0) atomicMax(&s_max[i], wmax);
+      }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < gc; i += kAssignThreads)
@@ -134,6 +143,12 @@ __global__ void __launch_bounds__(kAssignThreads) assign_pass2_kernel(AssignArgs
       for (int i = 0; i < gc; ++i) {
         const float gm = s_gtmax[i];
         if (!(gm >= a.min_pos)) continue;
+        if (gm > 0.0f) {   // a positive maximum can only be matched by an intersecting pair
+          const float4 g = s_gt[i];
+          const float iw = __fadd_rn(__fsub_rn(fminf(me.z, g.z), fmaxf(me.x, g.x)), a.delta);
+          const float ih = __fadd_rn(__fsub_rn(fminf(me.w, g.w), fmaxf(me.y, g.y)), a.delta);
+          if (!(iw > 0.0f && ih > 0.0f)) continue;
+        }
         if (iou_spec_d(me, area, s_gt[i], s_area[i], a.delta) == gm) result = g0 + i + 1;
       }
     }

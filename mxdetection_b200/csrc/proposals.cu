@@ -25,9 +25,14 @@ struct CollectArgs {
   int* num_valid;        // (B)
 };
 
+// The per-level keep lists are already in (score desc, index asc) order, so the per-image top max_num
+// needs no sort: the global rank of candidate (level l, position p) is p plus, for every other level,
+// the number of its candidates that precede it in the total order (score desc, concat index asc) -
+// a binary search per level in shared memory.  Rows with rank < max_num are written straight to
+// out[rank]; bit-identical to a stable sort of the concatenation.
 __global__ void __launch_bounds__(kCollectThreads, 1) rpn_collect_kernel(CollectArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64* keys = reinterpret_cast<u64*>(smem_raw);
+  float* sc = reinterpret_cast<float*>(smem_raw);     // concatenated kept scores (<= MXD_SORT_CAP)
   __shared__ int s_off[MXD_MAX_LEVELS + 1];
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid == 0) {
@@ -41,37 +46,45 @@ __global__ void __launch_bounds__(kCollectThreads, 1) rpn_collect_kernel(Collect
   __syncthreads();
   const int total = s_off[a.L];
   float* out = a.out + (size_t)b * a.max_num * 5;
-  const bool need_sort = total > a.max_num;
-  const int nout = need_sort ? a.max_num : total;
-  int P = 0;
-  if (need_sort) {
-    P = next_pow2(total);
-    for (int l = 0; l < a.L; ++l) {
-      const int s = b * a.L + l, cnt = s_off[l + 1] - s_off[l];
-      for (int j = tid; j < cnt; j += kCollectThreads) {
-        const int pos = a.keep[(size_t)s * a.keep_stride + j];
-        const int ci = s_off[l] + j;
-        keys[ci] = ((u64)f32_orderable(a.vals[(size_t)s * a.kmax + pos]) << 32) | (u64)(uint32_t)(total - 1 - ci);
-      }
-    }
-    for (int i = total + tid; i < P; i += kCollectThreads) keys[i] = 0;
-    __syncthreads();
-    bitonic_sort_desc(keys, P);
+  const int nout = min(total, a.max_num);
+  for (int l = 0; l < a.L; ++l) {
+    const int s = b * a.L + l, cnt = s_off[l + 1] - s_off[l];
+    for (int j = tid; j < cnt; j += kCollectThreads)
+      sc[s_off[l] + j] = a.vals[(size_t)s * a.kmax + a.keep[(size_t)s * a.keep_stride + j]] + 0.0f;   // -0 -> +0
   }
-  for (int r = tid; r < a.max_num; r += kCollectThreads) {
-    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-    float sc = 0.f;
-    if (r < nout) {
-      const int ci = need_sort ? total - 1 - (int)(uint32_t)keys[r] : r;
-      int l = 0;
-      while (l + 1 < a.L && ci >= s_off[l + 1]) ++l;
+  for (int r = nout + tid; r < a.max_num; r += kCollectThreads) {
+    float* o = out + (size_t)r * 5;
+    o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
+  }
+  __syncthreads();
+  for (int ci = tid; ci < total; ci += kCollectThreads) {
+    int l = 0;
+    while (l + 1 < a.L && ci >= s_off[l + 1]) ++l;
+    const float v = sc[ci];
+    int rank = ci - s_off[l];
+    if (total > a.max_num) {
+      for (int m = 0; m < a.L; ++m) {
+        if (m == l) continue;
+        // number of entries of list m with score > v (m > l) or >= v (m < l); lists are descending
+        int lo = s_off[m], hi = s_off[m + 1];
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          const float x = sc[mid];
+          const bool before = (m < l) ? (x >= v) : (x > v);
+          if (before) lo = mid + 1; else hi = mid;
+        }
+        rank += lo - s_off[m];
+      }
+    } else {
+      rank = ci;
+    }
+    if (rank < a.max_num) {
       const int s = b * a.L + l;
       const int pos = a.keep[(size_t)s * a.keep_stride + (ci - s_off[l])];
-      bx = a.boxes[(size_t)s * a.kmax + pos];
-      sc = a.vals[(size_t)s * a.kmax + pos];
+      const float4 bx = a.boxes[(size_t)s * a.kmax + pos];
+      float* o = out + (size_t)rank * 5;
+      o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = a.vals[(size_t)s * a.kmax + pos];
     }
-    float* o = out + (size_t)r * 5;
-    o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = sc;
   }
   if (tid == 0) a.num_valid[b] = nout;
 }
@@ -207,7 +220,7 @@ int mxd_rpn_proposals(const DLTensor* const* scores, const DLTensor* const* delt
   c.boxes = w.boxes; c.vals = w.vals; c.keep = w.keep; c.keep_cnt = w.keep_cnt;
   c.L = L; c.kmax = km; c.keep_stride = ks; c.max_num = cfg->max_num;
   c.out = dptr<float>(proposals); c.num_valid = dptr<int>(num_valid);
-  const int smem = MXD_SORT_CAP * (int)sizeof(u64);
+  const int smem = MXD_SORT_CAP * (int)sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     MXD_CUDA_OK(cudaFuncSetAttribute(rpn_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
