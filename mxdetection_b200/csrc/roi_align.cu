@@ -171,7 +171,9 @@ extern "C" {
 size_t mxd_roi_align_workspace_bytes(int num_rois, int batch, int channels, int num_levels, const int* feat_h,
                                      const int* feat_w, int pooled_h, int pooled_w, int sample_ratio) {
   if (num_levels < 1 || num_levels > MXD_MAX_LEVELS || !feat_h || !feat_w) return 0;
-  return plane_workspace_bytes(num_rois, batch, num_levels, feat_h, feat_w, channels, pooled_h, pooled_w, sample_ratio);
+  const size_t a = plane_workspace_bytes(num_rois, batch, num_levels, feat_h, feat_w, channels, pooled_h, pooled_w, sample_ratio);
+  const size_t b = tile_bwd_workspace_bytes(num_rois, batch, num_levels, feat_h, feat_w, channels, pooled_h, pooled_w, sample_ratio);
+  return a > b ? a : b;
 }
 
 int mxd_roi_align_fpn_forward(const DLTensor* const* feats, int num_levels, const float* spatial_scales,
@@ -203,6 +205,9 @@ int mxd_roi_align_fpn_backward(const DLTensor* grad_out, const DLTensor* rois, c
   const int* lv = levels ? dptr<int>(levels) : nullptr;
   if (workspace) {
     int handled = 0;
+    if ((rc = tile_backward(d, dptr<float>(rois), lv, dptr<float>(grad_out), R, pooled_h, pooled_w, sample_ratio,
+                            finest_scale, accumulate, workspace, workspace_bytes, st, &handled))) return rc;
+    if (handled) return MXD_OK;
     if ((rc = plane_backward(d, dptr<float>(rois), lv, dptr<float>(grad_out), R, pooled_h, pooled_w, sample_ratio,
                              finest_scale, accumulate, workspace, workspace_bytes, st, &handled))) return rc;
     if (handled) return MXD_OK;

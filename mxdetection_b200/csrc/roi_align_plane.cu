@@ -19,10 +19,9 @@
 //    batch index are few; the same kernel processes them afterwards with the
 //    generic global-memory gather (gather_roi_chunk).
 #include "roi_align.cuh"
+#include "ptx.cuh"
 
 namespace mxd {
-
-typedef unsigned long long u64;
 
 constexpr int kSmemLimit = 227 * 1024;       // per-CTA opt-in maximum on sm_100
 constexpr int kBigRing = 14 * 1024;          // table area in one-CTA-per-SM mode: leaves 54400 floats = a 200x272 plane
@@ -242,33 +241,6 @@ __global__ void __launch_bounds__(1024) plan_group_kernel(PlanCfg c, PlanWs w, i
   }
 }
 
-// -------------------------------------------------------------- PTX helpers ------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, u64* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-
 __device__ __forceinline__ float ldf(const char* p) { return *reinterpret_cast<const float*>(p); }
 
 struct ItemDesc { int lvl, img, band, cgi; };
@@ -302,12 +274,6 @@ struct SmemCtl {
   ItemSlot item;
 };
 
-__device__ __forceinline__ void mbar_arrive(u64* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void consumer_sync(int nthreads) {
-  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-}
 
 // Producer warp of the persistent kernels: pulls items off the global counter, waits until the
 // consumers released the band buffer, publishes the item descriptor and issues the TMA band loads.

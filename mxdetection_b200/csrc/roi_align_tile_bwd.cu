@@ -1,0 +1,542 @@
+// Tile-resident RoIAlign backward for B200 (Spec A backward, Spec G).
+//
+// Contract: _backward_ROIAlign of mxnet 1.3.0 as used by mxdetection/ops
+// (/root/reference/README.md:24) and SingleLevelRoI (/root/reference/README.md:32).
+//
+// Why: global RED.ADD is bound at ~200 G sector-ops/s on B200 (profiles/microbench), which
+// caps an atomic scatter at ~0.5 ms on BASELINE config 3; shared-memory fp32 atomics are CAS
+// loops.  This kernel needs neither:
+//
+//  * every gradient map is cut into tiles of <= 31 rows x 48 columns x 32 channels that live in
+//    shared memory as [pixel][33 words] (channel innermost).  Lane = channel, so all 32 lanes of
+//    a warp run the same control flow with warp-uniform weights, and every shared-memory access
+//    is bank-conflict free;
+//  * warp w of the CTA OWNS tile row w (fixed row pitch, whatever the level): only that warp ever
+//    touches it, so the accumulation is a plain LDS / FFMA / STS - no atomics and no barrier at all;
+//  * the planner (one warp per RoI) turns Spec A's 2 x PH*sr row taps into a dense per-row
+//    table (first bin, up to 7 bin weights), lists the RoIs intersecting every tile, and packs
+//    the x taps; a producer warp streams, per (RoI, tile) pair, the RoI's 32-channel slice of
+//    grad_out (one TMA bulk copy, read as g[lane*bins + bin]: conflict free because bins is
+//    odd), the row-table slice and the tile-relative x taps through an mbarrier ring;
+//  * each tile is written to HBM exactly once with plain coalesced stores (req=write needs no
+//    memset; req=add adds on the way out).
+//
+// RoIs that sample outside the image, are taller than 64 feature rows or have degenerate bins
+// take the generic RED path afterwards (gather_roi_chunk<true>) - they are rare.
+#include "roi_align.cuh"
+#include "ptx.cuh"
+
+namespace mxd {
+
+constexpr int kTbWarps = 31;                       // consumer warps; warp w owns tile row w
+constexpr int kTbThreads = (kTbWarps + 1) * 32;    // + one producer warp
+constexpr int kTbStages = 5;
+constexpr int kTbMaxHf = 64;                       // rows of the dense per-RoI row table
+constexpr int kTbPix = 33;                         // words per tile pixel (32 channels + 1 pad)
+constexpr int kTbMaxTiles = 32;                    // tiles one RoI may intersect
+constexpr int kTbMaxTh = kTbWarps;
+constexpr int kTbMaxTw = 48;
+constexpr int kTbRowWords = (kTbMaxTw + 1) * kTbPix;   // fixed row pitch: 48 columns + the trash column
+constexpr int kTbTrash = kTbMaxTw * kTbPix * 4;        // byte offset of the trash pixel inside a row
+constexpr int kTbSmem = 227 * 1024;
+
+enum { kMsgPair = 0, kMsgBegin = 1, kMsgZero = 2, kMsgStop = 3 };
+
+struct TLevel { int H, W, th, tw, nty, ntx, tile_base; };
+
+struct TCfg {
+  TLevel lv[MXD_MAX_LEVELS];
+  int L, N, C, PH, PW, sr, ty, tx, bins;
+  int tiles_per_img, NT, ncg, n_items;
+  int stage_bytes, off_xt, off_rt, off_g, tile_bytes, smem_bytes;
+  int accumulate;
+  float finest, inv_count;
+};
+
+struct TWs {
+  int* hdr;        // [0] item counter, [1] fallback count
+  int* cnt;        // [NT] RoIs per tile
+  int* cursor;     // [NT]
+  int* start;      // [NT]
+  int* fb_list;    // [R]
+  int4* roihdr;    // [R][2]  {y0, Hf, x0, x1} {b, lvl, ok, ntiles}
+  uint2* xtab;     // [R][tx] {column of the low tap (unclamped form), weight of the high tap}
+  uint4* rowtab;   // [R][kTbMaxHf][2]  {first bin | nbins<<8, w0..w6}
+  int* pairs;      // [R * kTbMaxTiles]
+  size_t bytes;
+};
+
+static TWs carve_tile(void* base, int R, int NT, int tx) {
+  TWs w;
+  size_t off = 0;
+  const size_t r1 = (size_t)(R > 0 ? R : 1);
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (char*)base + o; };
+  w.hdr = (int*)take(sizeof(int) * 64);
+  w.cnt = (int*)take(sizeof(int) * (size_t)NT);
+  w.cursor = (int*)take(sizeof(int) * (size_t)NT);
+  w.start = (int*)take(sizeof(int) * (size_t)NT);
+  w.fb_list = (int*)take(sizeof(int) * r1);
+  w.roihdr = (int4*)take(sizeof(int4) * 2 * r1);
+  w.xtab = (uint2*)take(sizeof(uint2) * r1 * tx);
+  w.rowtab = (uint4*)take(sizeof(uint4) * 2 * r1 * kTbMaxHf);
+  w.pairs = (int*)take(sizeof(int) * r1 * kTbMaxTiles);
+  w.bytes = off;
+  return w;
+}
+
+// Host: tile geometry per level for the shared-memory budget.  Only the (7x7, sample_ratio 2)-shaped
+// instantiations exist; everything else keeps the RED kernels.
+static bool make_tcfg(int N, int C, int L, const int* Hs, const int* Ws, int PH, int PW, int sr, float finest,
+                      int accumulate, TCfg* c) {
+  if (sr != 2 || PH != 7 || PW != 7 || (C & 31) != 0 || C == 0) return false;
+  memset(c, 0, sizeof(*c));
+  c->L = L; c->N = N; c->C = C; c->PH = PH; c->PW = PW; c->sr = sr; c->ty = PH * sr; c->tx = PW * sr;
+  c->bins = PH * PW; c->finest = finest; c->inv_count = 1.0f / (float)(sr * sr); c->accumulate = accumulate;
+  c->off_xt = 32;                                   // PW x {w0..w3}, then PW x {off0..off3}
+  c->off_rt = (int)align_up((size_t)c->off_xt + PW * 32, 32);
+  c->off_g = c->off_rt + kTbMaxTh * 32;
+  c->stage_bytes = (int)align_up((size_t)c->off_g + 32 * c->bins * 4, 128);
+  c->tile_bytes = (kTbSmem - kTbStages * c->stage_bytes - 256) & ~15;
+  const int max_rows = c->tile_bytes / (kTbRowWords * 4);
+  int base = 0;
+  for (int l = 0; l < L; ++l) {
+    TLevel& v = c->lv[l];
+    v.H = Hs[l]; v.W = Ws[l];
+    v.ntx = (v.W + kTbMaxTw - 1) / kTbMaxTw;
+    v.tw = (v.W + v.ntx - 1) / v.ntx;
+    int th_cap = max_rows;
+    if (th_cap > kTbMaxTh) th_cap = kTbMaxTh;
+    if (th_cap < 1) return false;
+    v.nty = (v.H + th_cap - 1) / th_cap;
+    v.th = (v.H + v.nty - 1) / v.nty;
+    v.tile_base = base;
+    base += v.nty * v.ntx;
+  }
+  c->tiles_per_img = base;
+  c->NT = N * base;
+  c->ncg = C / 32;
+  if ((long long)c->NT * c->ncg > 0x3fffffffLL) return false;
+  c->n_items = c->NT * c->ncg;
+  c->smem_bytes = c->tile_bytes + kTbStages * c->stage_bytes + 256;
+  return c->NT > 0;
+}
+
+// ------------------------------------------------------------------- planner ------
+// One warp per RoI: Spec A sample tables -> dense row table, packed x taps, tile counts.
+__global__ void __launch_bounds__(256) tplan_rois_kernel(FpnDesc d, TCfg c, TWs w, const float* __restrict__ rois,
+                                                          const int* __restrict__ levels, int R) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= R) return;
+  const unsigned full = 0xffffffffu;
+  const RoiGeom g = roi_geom(d, rois, levels, n, c.PH, c.PW, c.sr, c.finest);
+  bool ok = g.ok && g.H >= 2 && g.W >= 2;
+  int ylo = 0x3fffffff, xlo = 0x3fffffff;
+  float yl = 0.0f, xl = 0.0f;
+  bool valid = true;
+  if (lane < c.ty) {
+    const AxisTap a = axis_tap(g.rsh, g.bh, c.sr, lane / c.sr, lane % c.sr, g.H, 1);
+    valid = valid && a.valid;
+    const bool cl = a.hi == a.lo;      // clamped at the border -> unclamped form (size-2, l = 1)
+    ylo = cl ? a.lo - 1 : a.lo;
+    yl = cl ? 1.0f : a.l;
+  }
+  if (lane < c.tx) {
+    const AxisTap a = axis_tap(g.rsw, g.bw, c.sr, lane / c.sr, lane % c.sr, g.W, 1);
+    valid = valid && a.valid;
+    const bool cl = a.hi == a.lo;
+    xlo = cl ? a.lo - 1 : a.lo;
+    xl = cl ? 1.0f : a.l;
+  }
+  ok = ok && __all_sync(full, valid);
+  const int y0 = __reduce_min_sync(full, ylo);
+  const int y1 = __reduce_max_sync(full, lane < c.ty ? ylo + 1 : -1);
+  const int x0 = __reduce_min_sync(full, xlo);
+  const int x1 = __reduce_max_sync(full, lane < c.tx ? xlo + 1 : -1);
+  const int Hf = y1 - y0 + 1;
+  ok = ok && Hf >= 1 && Hf <= kTbMaxHf && y0 >= 0 && x0 >= 0;
+  bool rows_ok = true;
+  if (ok) {
+    for (int i0 = 0; i0 < Hf; i0 += 32) {
+      const int i = i0 + lane;
+      const int row = y0 + i;
+      int pa = -1, pl = -1;
+      float wr[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int t = 0; t < c.ty; ++t) {
+        const int lo_t = __shfl_sync(full, ylo, t);
+        const float l_t = __shfl_sync(full, yl, t);
+        float wt = 0.0f;
+        if (lo_t == row) wt = 1.0f - l_t;
+        else if (lo_t + 1 == row) wt = l_t;
+        if (wt != 0.0f) {
+          const int ph = t / c.sr;
+          if (pa < 0) pa = ph;
+          const int k = ph - pa;
+          if (k < 7) wr[k] += wt; else rows_ok = false;
+          pl = ph;
+        }
+      }
+      if (i < Hf) {
+        const int nph = pa < 0 ? 0 : pl - pa + 1;
+        uint4* rec = w.rowtab + ((size_t)n * kTbMaxHf + i) * 2;
+        rec[0] = make_uint4((unsigned)(pa < 0 ? 0 : pa) | ((unsigned)nph << 8), __float_as_uint(wr[0]),
+                            __float_as_uint(wr[1]), __float_as_uint(wr[2]));
+        rec[1] = make_uint4(__float_as_uint(wr[3]), __float_as_uint(wr[4]), __float_as_uint(wr[5]),
+                            __float_as_uint(wr[6]));
+      }
+    }
+  }
+  ok = ok && __all_sync(full, rows_ok);
+  int tya = 0, tyb = 0, txa = 0, txb = 0, nt = 0;
+  if (ok) {
+    const TLevel& v = c.lv[g.lvl];
+    tya = y0 / v.th; tyb = y1 / v.th; txa = x0 / v.tw; txb = x1 / v.tw;
+    nt = (tyb - tya + 1) * (txb - txa + 1);
+    if (nt > kTbMaxTiles) ok = false;
+  }
+  if (!ok) {
+    if (lane == 0) {
+      w.roihdr[(size_t)n * 2 + 1] = make_int4(0, 0, 0, 0);
+      w.fb_list[atomicAdd(&w.hdr[1], 1)] = n;
+    }
+    return;
+  }
+  if (lane < c.tx) w.xtab[(size_t)n * c.tx + lane] = make_uint2((unsigned)xlo, __float_as_uint(xl));
+  const TLevel& v = c.lv[g.lvl];
+  const int ncol = txb - txa + 1;
+  for (int q = lane; q < nt; q += 32) {
+    const int t = g.b * c.tiles_per_img + v.tile_base + (tya + q / ncol) * v.ntx + (txa + q % ncol);
+    atomicAdd(&w.cnt[t], 1);
+  }
+  if (lane == 0) {
+    w.roihdr[(size_t)n * 2] = make_int4(y0, Hf, x0, x1);
+    w.roihdr[(size_t)n * 2 + 1] = make_int4(g.b, g.lvl, 1, nt);
+  }
+}
+
+// Exclusive scan of the tile counts and the per-tile RoI lists (single CTA).
+__global__ void __launch_bounds__(1024) tplan_group_kernel(TCfg c, TWs w, int R) {
+  __shared__ int s_part[1024];
+  const int tid = threadIdx.x;
+  const int per = (c.NT + 1023) / 1024;
+  int sum = 0;
+  for (int i = tid * per; i < min(c.NT, (tid + 1) * per); ++i) sum += w.cnt[i];
+  s_part[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = tid >= o ? s_part[tid - o] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int run = s_part[tid] - sum;
+  for (int i = tid * per; i < min(c.NT, (tid + 1) * per); ++i) {
+    w.start[i] = run;
+    run += w.cnt[i];
+  }
+  __syncthreads();
+  __threadfence_block();
+  for (int n = tid; n < R; n += 1024) {
+    const int4 h1 = w.roihdr[(size_t)n * 2 + 1];
+    if (!h1.z) continue;
+    const int4 h0 = w.roihdr[(size_t)n * 2];
+    const TLevel& v = c.lv[h1.y];
+    const int tya = h0.x / v.th, tyb = (h0.x + h0.y - 1) / v.th, txa = h0.z / v.tw, txb = h0.w / v.tw;
+    for (int ty = tya; ty <= tyb; ++ty)
+      for (int tx = txa; tx <= txb; ++tx) {
+        const int t = h1.x * c.tiles_per_img + v.tile_base + ty * v.ntx + tx;
+        w.pairs[w.start[t] + atomicAdd(&w.cursor[t], 1)] = n;
+      }
+  }
+}
+
+// --------------------------------------------------------------- main kernel ------
+struct TbCtl {
+  u64 full[kTbStages];
+  u64 empty[kTbStages];
+};
+
+// The 4 x taps of bin pw (2 samples x lo/hi) as up to 4 DISTINCT tile columns with merged weights
+// (already scaled by 1/count), so the consumer can issue the 4 loads before the 4 stores.  Columns
+// outside the tile, and unused slots, point at the row's trash pixel.
+__device__ __forceinline__ void tb_pack_bin(uint4 e, int tx0, int tw, float inv_count, float4* wout, uint4* oout) {
+  const int a = (int)e.x - tx0, b = (int)e.z - tx0;       // low-tap columns of samples A, B (b >= a)
+  const float lA = __uint_as_float(e.y) * inv_count, lB = __uint_as_float(e.w) * inv_count;
+  const float hA = inv_count - lA, hB = inv_count - lB;
+  int c0 = a, c1 = a + 1, c2, c3;
+  float w0 = hA, w1 = lA, w2, w3;
+  if (b == a) { w0 += hB; w1 += lB; c2 = -1; c3 = -1; w2 = 0.0f; w3 = 0.0f; }
+  else if (b == a + 1) { w1 += hB; c2 = b + 1; w2 = lB; c3 = -1; w3 = 0.0f; }
+  else { c2 = b; c3 = b + 1; w2 = hB; w3 = lB; }
+  auto off = [&](int cx) { return ((unsigned)cx < (unsigned)tw) ? (unsigned)(cx * kTbPix * 4) : (unsigned)kTbTrash; };
+  *wout = make_float4(w0, w1, w2, w3);
+  *oout = make_uint4(off(c0), off(c1), off(c2), off(c3));
+}
+
+__device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, const TWs& w,
+                                            const float* __restrict__ gout, unsigned char* stages, TbCtl* ctl,
+                                            int lane) {
+  const unsigned full = 0xffffffffu;
+  int m = 0;
+  const uint32_t g_bytes = (uint32_t)(32 * c.bins * 4);
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(&w.hdr[0], 1);
+    item = __shfl_sync(full, item, 0);
+    if (item >= c.n_items) break;
+    // item = ((b * ncg + cg) * tiles_per_img + t): all tiles of one (image, channel group) are neighbours,
+    // so the RoIs' grad_out slices are re-read from L2 while they are hot
+    const int t = item % c.tiles_per_img;
+    const int r = item / c.tiles_per_img;
+    const int cg = r % c.ncg, b = r / c.ncg;
+    int l = 0;
+    while (l + 1 < c.L && t >= c.lv[l + 1].tile_base) ++l;
+    const TLevel& v = c.lv[l];
+    const int tl = t - v.tile_base;
+    const int ty0 = (tl / v.ntx) * v.th, tx0 = (tl % v.ntx) * v.tw;
+    const int tile_id = b * c.tiles_per_img + t;
+    const int cnt = w.cnt[tile_id], start = w.start[tile_id];
+    if (cnt == 0 && c.accumulate) continue;    // req=add and nothing to add
+    {
+      const int s = m % kTbStages;
+      mbar_wait(&ctl->empty[s], (((uint32_t)m / kTbStages) & 1u) ^ 1u);
+      if (lane == 0) {
+        int4* hd = reinterpret_cast<int4*>(stages + (size_t)s * c.stage_bytes);
+        hd[0] = make_int4(cnt ? kMsgBegin : kMsgZero, l, b, cg * 32);
+        hd[1] = make_int4(ty0, tx0, 0, 0);
+        mbar_arrive(&ctl->full[s]);
+      }
+      ++m;
+    }
+    for (int base = 0; base < cnt; base += 32) {
+      const int nb = min(32, cnt - base);
+      const int my_n = lane < nb ? w.pairs[start + base + lane] : 0;
+      const int4 h0 = w.roihdr[(size_t)my_n * 2];
+      uint4 xe = make_uint4(0u, 0u, 0u, 0u);      // lane pw: samples 2pw, 2pw+1 of the next pair's RoI
+      {
+        const int n0 = __shfl_sync(full, my_n, 0);
+        if (lane < c.PW) xe = reinterpret_cast<const uint4*>(w.xtab + (size_t)n0 * c.tx)[lane];
+      }
+      for (int j = 0; j < nb; ++j) {
+        const int n = __shfl_sync(full, my_n, j);
+        const int y0 = __shfl_sync(full, h0.x, j), Hf = __shfl_sync(full, h0.y, j);
+        const uint4 xc = xe;
+        if (j + 1 < nb) {
+          const int n1 = __shfl_sync(full, my_n, j + 1);
+          if (lane < c.PW) xe = reinterpret_cast<const uint4*>(w.xtab + (size_t)n1 * c.tx)[lane];
+        }
+        const int s = m % kTbStages;
+        mbar_wait(&ctl->empty[s], (((uint32_t)m / kTbStages) & 1u) ^ 1u);
+        unsigned char* st = stages + (size_t)s * c.stage_bytes;
+        const int ra = max(y0, ty0) - ty0;
+        const int rb = min(y0 + Hf - 1, ty0 + v.th - 1) - ty0;
+        if (lane < c.PW)
+          tb_pack_bin(xc, tx0, v.tw, c.inv_count, reinterpret_cast<float4*>(st + c.off_xt) + lane,
+                      reinterpret_cast<uint4*>(st + c.off_xt + c.PW * 16) + lane);
+        if (lane == 0) reinterpret_cast<int4*>(st)[0] = make_int4(kMsgPair, ra, rb, n);
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t rt_bytes = (uint32_t)((rb - ra + 1) * 32);
+          mbar_arrive_expect_tx(&ctl->full[s], g_bytes + rt_bytes);
+          bulk_g2s(st + c.off_g, gout + ((size_t)n * c.C + cg * 32) * c.bins, g_bytes, &ctl->full[s]);
+          bulk_g2s(st + c.off_rt + ra * 32, w.rowtab + ((size_t)n * kTbMaxHf + (ra + ty0 - y0)) * 2, rt_bytes,
+                   &ctl->full[s]);
+        }
+        ++m;
+      }
+    }
+  }
+  const int s = m % kTbStages;
+  mbar_wait(&ctl->empty[s], (((uint32_t)m / kTbStages) & 1u) ^ 1u);
+  if (lane == 0) {
+    reinterpret_cast<int4*>(stages + (size_t)s * c.stage_bytes)[0] = make_int4(kMsgStop, 0, 0, 0);
+    mbar_arrive(&ctl->full[s]);
+  }
+}
+
+// One tile row of one RoI for this lane's channel: h[pw] = sum_ph Wy[row][ph] * g[ph][pw], then the
+// (up to) 4 distinct columns of every bin get w_k * h[pw] with plain read-modify-writes - the row
+// belongs to this warp, and distinct columns let the 4 loads issue before the 4 stores.
+template <int PW>
+__device__ __forceinline__ void tb_row(const float* __restrict__ gl, const uint4* __restrict__ rt,
+                                       const float4* __restrict__ xw, const uint4* __restrict__ xo, char* rowp) {
+  const uint4 q0 = rt[0];
+  const int nph = (int)((q0.x >> 8) & 0xffu);
+  if (nph == 0) return;
+  const uint4 q1 = rt[1];
+  const float wts[7] = {__uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w), __uint_as_float(q1.x),
+                        __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w)};
+  const float* gp = gl + (int)(q0.x & 0xffu) * PW;
+  float h[PW];
+#pragma unroll
+  for (int pw = 0; pw < PW; ++pw) h[pw] = wts[0] * gp[pw];
+#pragma unroll
+  for (int k = 1; k < 7; ++k) {
+    if (k < nph) {
+#pragma unroll
+      for (int pw = 0; pw < PW; ++pw) h[pw] = fmaf(wts[k], gp[k * PW + pw], h[pw]);
+    }
+  }
+#pragma unroll
+  for (int pw = 0; pw < PW; ++pw) {
+    const float4 wv = xw[pw];
+    const uint4 ov = xo[pw];
+    float* p0 = reinterpret_cast<float*>(rowp + ov.x);
+    float* p1 = reinterpret_cast<float*>(rowp + ov.y);
+    float* p2 = reinterpret_cast<float*>(rowp + ov.z);
+    float* p3 = reinterpret_cast<float*>(rowp + ov.w);
+    const float v0 = *p0, v1 = *p1, v2 = *p2, v3 = *p3;
+    const float hv = h[pw];
+    *p0 = fmaf(wv.x, hv, v0);
+    *p1 = fmaf(wv.y, hv, v1);
+    *p2 = fmaf(wv.z, hv, v2);
+    *p3 = fmaf(wv.w, hv, v3);
+  }
+}
+
+template <int PW>
+__global__ void __launch_bounds__(kTbThreads, 1)
+roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_constant__ TCfg c, TWs w,
+                          const float* __restrict__ gout) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* tile = reinterpret_cast<float*>(smem);
+  unsigned char* stages = smem + c.tile_bytes;
+  TbCtl* ctl = reinterpret_cast<TbCtl*>(smem + c.tile_bytes + (size_t)kTbStages * c.stage_bytes);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < kTbStages; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], kTbWarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == kTbWarps) {
+    tb_producer(d, c, w, gout, stages, ctl, lane);
+    return;
+  }
+  // ================================= consumer warps ====================================
+  // Warp w owns tile row w for the whole kernel (fixed pitch, independent of the level's tile shape): it
+  // zeroes it once, accumulates every RoI of the item into it, and writes + re-zeroes it at the item's end.
+  // No barrier ever: the only coupling between warps is the depth of the message ring.
+  float* trow = tile + (size_t)warp * kTbRowWords;
+  for (int i = lane; i < kTbRowWords; i += 32) trow[i] = 0.0f;
+  __syncwarp();
+  int m = 0;
+  bool have = false;
+  int lvl = 0, img = 0, c0 = 0, ty0 = 0, tx0 = 0, th = 0, tw = 0, H = 0, W = 0;
+  auto write_row = [&](bool zeros) {
+    const int gy = ty0 + warp;
+    if (warp >= th || gy >= H) return;
+    const int twe = min(tw, W - tx0);
+    const size_t plane = (size_t)H * W;
+    float* g0 = d.feat[lvl] + (((size_t)img * c.C + c0) * H + gy) * W + tx0;
+    const bool acc = c.accumulate != 0;
+    if (lane < twe) {                       // columns 0..31: lane = column, one channel per step
+      float* gp = g0 + lane;
+      float* tp = trow + lane * kTbPix;
+#pragma unroll 8
+      for (int ch = 0; ch < 32; ++ch) {
+        float v = 0.0f;
+        if (!zeros) { v = tp[ch]; tp[ch] = 0.0f; }
+        if (acc) v += *gp;
+        *gp = v;
+        gp += plane;
+      }
+    }
+    const int x2 = 32 + (lane & 15), chb = (lane >> 4) * 16;   // columns 32..47: two channels (ch, ch+16) per step
+    if (x2 < twe) {
+      float* gp = g0 + (size_t)chb * plane + x2;
+      float* tp = trow + x2 * kTbPix + chb;
+#pragma unroll 8
+      for (int ch = 0; ch < 16; ++ch) {
+        float v = 0.0f;
+        if (!zeros) { v = tp[ch]; tp[ch] = 0.0f; }
+        if (acc) v += *gp;
+        *gp = v;
+        gp += plane;
+      }
+    }
+    __syncwarp();
+  };
+  for (;;) {
+    const int s = m % kTbStages;
+    mbar_wait(&ctl->full[s], ((uint32_t)m / kTbStages) & 1u);
+    const unsigned char* st = stages + (size_t)s * c.stage_bytes;
+    const int4 hd = reinterpret_cast<const int4*>(st)[0];
+    if (hd.x == kMsgPair) {
+      if (warp >= hd.y && warp <= hd.z)
+        tb_row<PW>(reinterpret_cast<const float*>(st + c.off_g) + lane * c.bins,
+                   reinterpret_cast<const uint4*>(st + c.off_rt) + warp * 2,
+                   reinterpret_cast<const float4*>(st + c.off_xt),
+                   reinterpret_cast<const uint4*>(st + c.off_xt + PW * 16),
+                   reinterpret_cast<char*>(trow + lane));
+    } else {
+      if (have) write_row(false);
+      have = false;
+      if (hd.x == kMsgStop) break;
+      const int4 h1 = reinterpret_cast<const int4*>(st)[1];
+      lvl = hd.y; img = hd.z; c0 = hd.w; ty0 = h1.x; tx0 = h1.y;
+      th = c.lv[lvl].th; tw = c.lv[lvl].tw; H = c.lv[lvl].H; W = c.lv[lvl].W;
+      if (hd.x == kMsgBegin) have = true;
+      else write_row(true);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ctl->empty[s]);
+    ++m;
+  }
+}
+
+// RoIs the planner rejected: generic per-tap RED path, after the tiles are in HBM.
+__global__ void __launch_bounds__(256) tile_bwd_fallback_kernel(FpnDesc d, TCfg c, TWs w,
+                                                                 const float* __restrict__ rois,
+                                                                 const int* __restrict__ levels, float* gout) {
+  const int n_fb = w.hdr[1];
+  const int chunks = (c.C + 31) / 32;
+  for (int i = blockIdx.x; i < n_fb * chunks; i += gridDim.x) {
+    const int n = w.fb_list[i / chunks];
+    const int c0 = (i % chunks) * 32;
+    const RoiGeom g = roi_geom(d, rois, levels, n, c.PH, c.PW, c.sr, c.finest);
+    gather_roi_chunk<true>(d, g, n, c0, min(32, c.C - c0), gout, c.PH, c.PW, threadIdx.x, 256);
+  }
+}
+
+size_t tile_bwd_workspace_bytes(int R, int N, int L, const int* Hs, const int* Ws, int C, int PH, int PW, int sr) {
+  TCfg c;
+  if (!make_tcfg(N, C, L, Hs, Ws, PH, PW, sr, 56.0f, 0, &c)) return 0;
+  return carve_tile(nullptr, R, c.NT, c.tx).bytes;
+}
+
+int tile_backward(const FpnDesc& d, const float* rois, const int* levels, const float* gout, int R, int PH, int PW,
+                  int sr, float finest, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st, int* handled) {
+  *handled = 0;
+  TCfg c;
+  if (R == 0 || d.C == 0) return MXD_OK;
+  if (!make_tcfg(d.N, d.C, d.num_levels, d.H, d.W, PH, PW, sr, finest, accumulate, &c)) return MXD_OK;
+  if ((reinterpret_cast<uintptr_t>(gout) & 15) != 0) return MXD_OK;     // TMA source alignment
+  TWs w = carve_tile(ws, R, c.NT, c.tx);
+  MXD_REQUIRE(ws_bytes >= w.bytes, MXD_EWORKSPACE, "roi_align workspace %zu < %zu bytes", ws_bytes, w.bytes);
+  MXD_REQUIRE(((uintptr_t)ws & 255) == 0, MXD_EINVAL, "workspace must be 256-byte aligned");
+  int sms = 0, dev = 0;
+  MXD_CUDA_OK(cudaGetDevice(&dev));
+  MXD_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t zbytes = (size_t)((char*)w.start - (char*)w.hdr);    // hdr, cnt, cursor
+  MXD_CUDA_OK(cudaMemsetAsync(w.hdr, 0, zbytes, st));
+  tplan_rois_kernel<<<(R * 32 + 255) / 256, 256, 0, st>>>(d, c, w, rois, levels, R);
+  MXD_POST_LAUNCH("roi_align_tplan_rois");
+  tplan_group_kernel<<<1, 1024, 0, st>>>(c, w, R);
+  MXD_POST_LAUNCH("roi_align_tplan_group");
+  static bool attr_done = false;
+  if (!attr_done) {
+    MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_tile_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem));
+    attr_done = true;
+  }
+  roi_align_tile_bwd_kernel<7><<<sms, kTbThreads, c.smem_bytes, st>>>(d, c, w, gout);
+  MXD_POST_LAUNCH("roi_align_tile_bwd");
+  tile_bwd_fallback_kernel<<<2 * sms, 256, 0, st>>>(d, c, w, rois, levels, const_cast<float*>(gout));
+  MXD_POST_LAUNCH("roi_align_tile_bwd_fallback");
+  *handled = 1;
+  return MXD_OK;
+}
+
+}  // namespace mxd

@@ -91,6 +91,35 @@ def test_roi_align_vs_oracle_random(sr, ps, roi_path):
     assert close(N(acc), base + gref, 1e-4)
 
 
+@pytest.mark.parametrize("C,H,W,R", [(32, 50, 68, 96), (64, 100, 168, 300), (32, 13, 9, 40), (96, 70, 130, 64)])
+def test_roi_align_tile_backward_paths(C, H, W, R):
+    """Tile-resident backward (C % 32 == 0, 7x7, sr 2): tiny / huge / out-of-image RoIs (those take the RED
+    fallback after the tiles are written), partial edge tiles, req=write and req=add."""
+    from mxdetection_b200.ops import roi_align_backward
+    rng = np.random.default_rng(C + H + R)
+    Nn = 2
+    x1 = rng.uniform(-30, W * 4, R); y1 = rng.uniform(-30, H * 4, R)
+    w = np.exp(rng.uniform(np.log(1), np.log(4 * W), R)); h = np.exp(rng.uniform(np.log(1), np.log(4 * H), R))
+    rois = np.stack([rng.integers(0, Nn, R), x1, y1, x1 + w, y1 + h], 1).astype(F)
+    rois[0] = [0, 0, 0, 4 * W - 1, 4 * H - 1]          # whole map
+    rois[1] = [1, 8, 8, 8.5, 8.5]                        # degenerate: every sample in one pixel quad
+    rois[2] = [5, 0, 0, 10, 10]                          # bad batch index: no gradient
+    rois[3] = [0, 4 * W - 6, 4 * H - 6, 4 * W - 1, 4 * H - 1]   # clamped at the far border
+    gout = rng.standard_normal((R, C, 7, 7)).astype(F)
+    shape = (Nn, C, H, W)
+    gref = cref.roi_align_backward(gout, rois, shape, (7, 7), 0.25, 2)
+    gin = N(roi_align_backward(T(gout), T(rois), shape, (7, 7), 0.25, 2))
+    assert close(gin, gref, 1e-4)
+    base = rng.standard_normal(shape).astype(F)
+    acc = T(base.copy())
+    roi_align_backward(T(gout), T(rois), shape, (7, 7), 0.25, 2, grad_data=acc, accumulate=True)
+    assert close(N(acc), base + gref, 1e-4)
+    # no RoI at all on image 1: its tiles are still zero-filled under req=write
+    rois0 = rois.copy(); rois0[:, 0] = 0
+    g0 = N(roi_align_backward(T(gout), T(rois0), shape, (7, 7), 0.25, 2))
+    assert np.all(g0[1] == 0) and close(g0, cref.roi_align_backward(gout, rois0, shape, (7, 7), 0.25, 2), 1e-4)
+
+
 def test_roi_align_edge_cases(roi_path):
     from mxdetection_b200.ops import roi_align_forward, roi_align_backward
     data = np.random.default_rng(0).standard_normal((2, 3, 10, 12)).astype(F)
