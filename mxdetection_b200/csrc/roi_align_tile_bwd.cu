@@ -92,8 +92,8 @@ static bool make_tcfg(int N, int C, int L, const int* Hs, const int* Ws, int PH,
   memset(c, 0, sizeof(*c));
   c->L = L; c->N = N; c->C = C; c->PH = PH; c->PW = PW; c->sr = sr; c->ty = PH * sr; c->tx = PW * sr;
   c->bins = PH * PW; c->finest = finest; c->inv_count = 1.0f / (float)(sr * sr); c->accumulate = accumulate;
-  c->off_xt = 32;                                   // PW x {w0..w3}, then PW x {off0..off3}
-  c->off_rt = (int)align_up((size_t)c->off_xt + PW * 32, 32);
+  c->off_xt = 32;                                   // PW x {w1, w2, w3, 4 x u8 column}
+  c->off_rt = (int)align_up((size_t)c->off_xt + PW * 16, 32);
   c->off_g = c->off_rt + kTbMaxTh * 32;
   c->stage_bytes = (int)align_up((size_t)c->off_g + 32 * c->bins * 4, 128);
   c->tile_bytes = (kTbSmem - kTbStages * c->stage_bytes - 256) & ~15;
@@ -258,19 +258,21 @@ struct TbCtl {
 
 // The 4 x taps of bin pw (2 samples x lo/hi) as up to 4 DISTINCT tile columns with merged weights
 // (already scaled by 1/count), so the consumer can issue the 4 loads before the 4 stores.  Columns
-// outside the tile, and unused slots, point at the row's trash pixel.
-__device__ __forceinline__ void tb_pack_bin(uint4 e, int tx0, int tw, float inv_count, float4* wout, uint4* oout) {
+// outside the tile, and unused slots, are the row's trash column (index kTbMaxTw).  Packed to 16 bytes
+// (a uniform LDS.128 costs 2 shared-memory wavefronts, the scarce resource of this kernel):
+// {w1, w2, w3, c0 | c1<<8 | c2<<16 | c3<<24}; w0 = 2/count - (w1 + w2 + w3).
+__device__ __forceinline__ uint4 tb_pack_bin(uint4 e, int tx0, int tw, float inv_count) {
   const int a = (int)e.x - tx0, b = (int)e.z - tx0;       // low-tap columns of samples A, B (b >= a)
   const float lA = __uint_as_float(e.y) * inv_count, lB = __uint_as_float(e.w) * inv_count;
-  const float hA = inv_count - lA, hB = inv_count - lB;
+  const float hB = inv_count - lB;
   int c0 = a, c1 = a + 1, c2, c3;
-  float w0 = hA, w1 = lA, w2, w3;
-  if (b == a) { w0 += hB; w1 += lB; c2 = -1; c3 = -1; w2 = 0.0f; w3 = 0.0f; }
+  float w1 = lA, w2, w3;
+  if (b == a) { w1 += lB; c2 = -1; c3 = -1; w2 = 0.0f; w3 = 0.0f; }
   else if (b == a + 1) { w1 += hB; c2 = b + 1; w2 = lB; c3 = -1; w3 = 0.0f; }
   else { c2 = b; c3 = b + 1; w2 = hB; w3 = lB; }
-  auto off = [&](int cx) { return ((unsigned)cx < (unsigned)tw) ? (unsigned)(cx * kTbPix * 4) : (unsigned)kTbTrash; };
-  *wout = make_float4(w0, w1, w2, w3);
-  *oout = make_uint4(off(c0), off(c1), off(c2), off(c3));
+  auto col = [&](int cx) { return ((unsigned)cx < (unsigned)tw) ? (unsigned)cx : (unsigned)kTbMaxTw; };
+  return make_uint4(__float_as_uint(w1), __float_as_uint(w2), __float_as_uint(w3),
+                    col(c0) | (col(c1) << 8) | (col(c2) << 16) | (col(c3) << 24));
 }
 
 __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, const TWs& w,
@@ -301,9 +303,9 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
       const int s = m % kTbStages;
       mbar_wait(&ctl->empty[s], (((uint32_t)m / kTbStages) & 1u) ^ 1u);
       if (lane == 0) {
-        int4* hd = reinterpret_cast<int4*>(stages + (size_t)s * c.stage_bytes);
-        hd[0] = make_int4(cnt ? kMsgBegin : kMsgZero, l, b, cg * 32);
-        hd[1] = make_int4(ty0, tx0, 0, 0);
+        int* hd = reinterpret_cast<int*>(stages + (size_t)s * c.stage_bytes);
+        hd[0] = cnt ? kMsgBegin : kMsgZero;
+        reinterpret_cast<int4*>(hd)[1] = make_int4(l, b, cg * 32, ty0 | (tx0 << 16));
         mbar_arrive(&ctl->full[s]);
       }
       ++m;
@@ -312,6 +314,10 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
       const int nb = min(32, cnt - base);
       const int my_n = lane < nb ? w.pairs[start + base + lane] : 0;
       const int4 h0 = w.roihdr[(size_t)my_n * 2];
+      if (lane < nb)   // the slices of the next 32 pairs start their trip HBM -> L2 now
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gout + ((size_t)my_n * c.C + cg * 32) * c.bins),
+                     "r"(g_bytes)
+                     : "memory");
       uint4 xe = make_uint4(0u, 0u, 0u, 0u);      // lane pw: samples 2pw, 2pw+1 of the next pair's RoI
       {
         const int n0 = __shfl_sync(full, my_n, 0);
@@ -330,10 +336,8 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
         unsigned char* st = stages + (size_t)s * c.stage_bytes;
         const int ra = max(y0, ty0) - ty0;
         const int rb = min(y0 + Hf - 1, ty0 + v.th - 1) - ty0;
-        if (lane < c.PW)
-          tb_pack_bin(xc, tx0, v.tw, c.inv_count, reinterpret_cast<float4*>(st + c.off_xt) + lane,
-                      reinterpret_cast<uint4*>(st + c.off_xt + c.PW * 16) + lane);
-        if (lane == 0) reinterpret_cast<int4*>(st)[0] = make_int4(kMsgPair, ra, rb, n);
+        if (lane < c.PW) reinterpret_cast<uint4*>(st + c.off_xt)[lane] = tb_pack_bin(xc, tx0, v.tw, c.inv_count);
+        if (lane == 0) reinterpret_cast<int*>(st)[0] = kMsgPair | (ra << 8) | (rb << 16);
         __syncwarp();
         if (lane == 0) {
           const uint32_t rt_bytes = (uint32_t)((rb - ra + 1) * 32);
@@ -349,7 +353,7 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
   const int s = m % kTbStages;
   mbar_wait(&ctl->empty[s], (((uint32_t)m / kTbStages) & 1u) ^ 1u);
   if (lane == 0) {
-    reinterpret_cast<int4*>(stages + (size_t)s * c.stage_bytes)[0] = make_int4(kMsgStop, 0, 0, 0);
+    reinterpret_cast<int*>(stages + (size_t)s * c.stage_bytes)[0] = kMsgStop;
     mbar_arrive(&ctl->full[s]);
   }
 }
@@ -358,39 +362,55 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
 // (up to) 4 distinct columns of every bin get w_k * h[pw] with plain read-modify-writes - the row
 // belongs to this warp, and distinct columns let the 4 loads issue before the 4 stores.
 template <int PW>
-__device__ __forceinline__ void tb_row(const float* __restrict__ gl, const uint4* __restrict__ rt,
-                                       const float4* __restrict__ xw, const uint4* __restrict__ xo, char* rowp) {
-  const uint4 q0 = rt[0];
+__device__ __forceinline__ void tb_row(const float* __restrict__ gl, const uint2* __restrict__ rt,
+                                       const uint4* __restrict__ xt, char* rowp, float two_ic) {
+  const uint2 q0 = rt[0];                    // {first bin | nbins << 8, w0}
   const int nph = (int)((q0.x >> 8) & 0xffu);
   if (nph == 0) return;
-  const uint4 q1 = rt[1];
-  const float wts[7] = {__uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w), __uint_as_float(q1.x),
-                        __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w)};
   const float* gp = gl + (int)(q0.x & 0xffu) * PW;
   float h[PW];
+  {
+    const float w0 = __uint_as_float(q0.y);
 #pragma unroll
-  for (int pw = 0; pw < PW; ++pw) h[pw] = wts[0] * gp[pw];
+    for (int pw = 0; pw < PW; ++pw) h[pw] = w0 * gp[pw];
+  }
+  if (nph > 1) {
+    const uint2 q1 = rt[1];                  // {w1, w2}
+    const float w1 = __uint_as_float(q1.x);
 #pragma unroll
-  for (int k = 1; k < 7; ++k) {
-    if (k < nph) {
+    for (int pw = 0; pw < PW; ++pw) h[pw] = fmaf(w1, gp[PW + pw], h[pw]);
+    if (nph > 2) {
+      const float w2 = __uint_as_float(q1.y);
 #pragma unroll
-      for (int pw = 0; pw < PW; ++pw) h[pw] = fmaf(wts[k], gp[k * PW + pw], h[pw]);
+      for (int pw = 0; pw < PW; ++pw) h[pw] = fmaf(w2, gp[2 * PW + pw], h[pw]);
+      if (nph > 3) {
+        const uint4 q2 = reinterpret_cast<const uint4*>(rt)[1];   // {w3..w6}
+        const float wk[4] = {__uint_as_float(q2.x), __uint_as_float(q2.y), __uint_as_float(q2.z), __uint_as_float(q2.w)};
+#pragma unroll
+        for (int k = 3; k < 7; ++k) {
+          if (k < nph) {
+#pragma unroll
+            for (int pw = 0; pw < PW; ++pw) h[pw] = fmaf(wk[k - 3], gp[k * PW + pw], h[pw]);
+          }
+        }
+      }
     }
   }
 #pragma unroll
   for (int pw = 0; pw < PW; ++pw) {
-    const float4 wv = xw[pw];
-    const uint4 ov = xo[pw];
-    float* p0 = reinterpret_cast<float*>(rowp + ov.x);
-    float* p1 = reinterpret_cast<float*>(rowp + ov.y);
-    float* p2 = reinterpret_cast<float*>(rowp + ov.z);
-    float* p3 = reinterpret_cast<float*>(rowp + ov.w);
+    const uint4 e = xt[pw];
+    const float w1 = __uint_as_float(e.x), w2 = __uint_as_float(e.y), w3 = __uint_as_float(e.z);
+    const float w0 = two_ic - ((w1 + w2) + w3);
+    float* p0 = reinterpret_cast<float*>(rowp + (e.w & 0xffu) * (kTbPix * 4));
+    float* p1 = reinterpret_cast<float*>(rowp + ((e.w >> 8) & 0xffu) * (kTbPix * 4));
+    float* p2 = reinterpret_cast<float*>(rowp + ((e.w >> 16) & 0xffu) * (kTbPix * 4));
+    float* p3 = reinterpret_cast<float*>(rowp + (e.w >> 24) * (kTbPix * 4));
     const float v0 = *p0, v1 = *p1, v2 = *p2, v3 = *p3;
     const float hv = h[pw];
-    *p0 = fmaf(wv.x, hv, v0);
-    *p1 = fmaf(wv.y, hv, v1);
-    *p2 = fmaf(wv.z, hv, v2);
-    *p3 = fmaf(wv.w, hv, v3);
+    *p0 = fmaf(w0, hv, v0);
+    *p1 = fmaf(w1, hv, v1);
+    *p2 = fmaf(w2, hv, v2);
+    *p3 = fmaf(w3, hv, v3);
   }
 }
 
@@ -463,22 +483,22 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
     const int s = m % kTbStages;
     mbar_wait(&ctl->full[s], ((uint32_t)m / kTbStages) & 1u);
     const unsigned char* st = stages + (size_t)s * c.stage_bytes;
-    const int4 hd = reinterpret_cast<const int4*>(st)[0];
-    if (hd.x == kMsgPair) {
-      if (warp >= hd.y && warp <= hd.z)
+    const int hd = reinterpret_cast<const int*>(st)[0];
+    const int kind = hd & 0xff;
+    if (kind == kMsgPair) {
+      if (warp >= ((hd >> 8) & 0xff) && warp <= (hd >> 16))
         tb_row<PW>(reinterpret_cast<const float*>(st + c.off_g) + lane * c.bins,
-                   reinterpret_cast<const uint4*>(st + c.off_rt) + warp * 2,
-                   reinterpret_cast<const float4*>(st + c.off_xt),
-                   reinterpret_cast<const uint4*>(st + c.off_xt + PW * 16),
-                   reinterpret_cast<char*>(trow + lane));
+                   reinterpret_cast<const uint2*>(st + c.off_rt) + warp * 4,
+                   reinterpret_cast<const uint4*>(st + c.off_xt), reinterpret_cast<char*>(trow + lane),
+                   2.0f * c.inv_count);
     } else {
       if (have) write_row(false);
       have = false;
-      if (hd.x == kMsgStop) break;
+      if (kind == kMsgStop) break;
       const int4 h1 = reinterpret_cast<const int4*>(st)[1];
-      lvl = hd.y; img = hd.z; c0 = hd.w; ty0 = h1.x; tx0 = h1.y;
+      lvl = h1.x; img = h1.y; c0 = h1.z; ty0 = h1.w & 0xffff; tx0 = h1.w >> 16;
       th = c.lv[lvl].th; tw = c.lv[lvl].tw; H = c.lv[lvl].H; W = c.lv[lvl].W;
-      if (hd.x == kMsgBegin) have = true;
+      if (kind == kMsgBegin) have = true;
       else write_row(true);
     }
     __syncwarp();
