@@ -30,7 +30,7 @@ namespace mxd {
 
 constexpr int kTbWarps = 31;                       // consumer warps; warp w owns tile row w
 constexpr int kTbThreads = (kTbWarps + 1) * 32;    // + one producer warp
-constexpr int kTbStages = 5;
+constexpr int kTbStages = 9;
 constexpr int kTbMaxHf = 64;                       // rows of the dense per-RoI row table
 constexpr int kTbPix = 33;                         // words per tile pixel (32 channels + 1 pad)
 constexpr int kTbMaxTiles = 32;                    // tiles one RoI may intersect
@@ -48,7 +48,7 @@ struct TCfg {
   TLevel lv[MXD_MAX_LEVELS];
   int L, N, C, PH, PW, sr, ty, tx, bins;
   int tiles_per_img, NT, ncg, n_items;
-  int stage_bytes, off_xt, off_rt, off_g, tile_bytes, smem_bytes;
+  int stage_bytes, off_xt, off_rt, off_g, tile_bytes, smem_bytes, max_rows;
   int accumulate;
   float finest, inv_count;
 };
@@ -98,6 +98,7 @@ static bool make_tcfg(int N, int C, int L, const int* Hs, const int* Ws, int PH,
   c->stage_bytes = (int)align_up((size_t)c->off_g + 32 * c->bins * 4, 128);
   c->tile_bytes = (kTbSmem - kTbStages * c->stage_bytes - 256) & ~15;
   const int max_rows = c->tile_bytes / (kTbRowWords * 4);
+  c->max_rows = max_rows;
   int base = 0;
   for (int l = 0; l < L; ++l) {
     TLevel& v = c->lv[l];
@@ -439,8 +440,9 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
   // Warp w owns tile row w for the whole kernel (fixed pitch, independent of the level's tile shape): it
   // zeroes it once, accumulates every RoI of the item into it, and writes + re-zeroes it at the item's end.
   // No barrier ever: the only coupling between warps is the depth of the message ring.
-  float* trow = tile + (size_t)warp * kTbRowWords;
-  for (int i = lane; i < kTbRowWords; i += 32) trow[i] = 0.0f;
+  float* trow = tile + (size_t)(warp < c.max_rows ? warp : 0) * kTbRowWords;   // warps >= max_rows never own a row
+  if (warp < c.max_rows)
+    for (int i = lane; i < kTbRowWords; i += 32) trow[i] = 0.0f;
   __syncwarp();
   int m = 0;
   bool have = false;
