@@ -472,6 +472,143 @@ roi_align_plane_fwd_kernel(const __grid_constant__ FpnDesc d, const __grid_const
   }
 }
 
+// ------------------------------------------------- forward, 7x7 / sample_ratio 2 ---
+// Specialisation for the detector's bbox RoIAlign (2 * PW * sr = 28 x taps <= 32 lanes).  Measured on the
+// generic kernel above: two 16-lane jobs per warp read different rows in one LDS and collide on banks
+// (1.7 wavefronts per LDS), and the LSU data pipe - not issue - bounds the kernel.  Here ONE (RoI, channel)
+// job owns the warp and lane l is x TAP l (sample l>>1, low/high tap l&1): all 28 taps of a sample row are
+// one conflict-free LDS (<= 32 consecutive columns of one row), lane weights are per-lane registers, and the
+// 4 lanes of a bin are folded with a 6-shuffle transposing butterfly that leaves every lane with at most
+// two finished bins to store.
+template <int PH, int PW>
+__global__ void __launch_bounds__(1024, 1)
+roi_align_plane_fwd_tap_kernel(const __grid_constant__ FpnDesc d, const __grid_constant__ PlanCfg c, PlanWs w,
+                               const float* __restrict__ rois, const int* __restrict__ levels,
+                               float* __restrict__ out) {
+  static_assert(4 * PW <= 32 && PH <= 8, "lane = x tap, 8 accumulators");
+  constexpr int TY = 2 * PH, TX = 2 * PW, ENT = TY + TX, BINS = PH * PW;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* buf = reinterpret_cast<float*>(smem);
+  uint2* tab_all = reinterpret_cast<uint2*>(smem + (size_t)c.budget_floats * 4);
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + (size_t)c.budget_floats * 4 + c.tab_bytes);
+  const int tid = threadIdx.x;
+  const int Tc = blockDim.x - 32;            // consumer threads; the last warp is the producer
+  const int n_cwarps = Tc >> 5;
+  if (tid == 0) {
+    mbar_init(&ctl->desc_full, 1);
+    mbar_init(&ctl->band_full, 1);
+    mbar_init(&ctl->band_empty, n_cwarps);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid >= Tc) {
+    plane_producer(d, c, w, ctl, buf, tid - Tc, true);
+    return;
+  }
+  const int cw = tid >> 5, lane = tid & 31;
+  uint2* slot = tab_all + cw * 16;           // this warp's copy of the current RoI's TY y entries
+  const uint4* slot4 = reinterpret_cast<const uint4*>(slot);
+  const int xs = min(lane >> 1, TX - 1);     // x sample of this lane
+  const bool lane_on = lane < 2 * TX;
+  const int t4 = lane & 3, pw = min(lane >> 2, PW - 1);
+  const bool odd = lane & 1, up = lane & 2;
+  const int o0 = t4 * PW + pw, o1 = (t4 + 4) * PW + pw;
+  const bool st0 = lane_on && t4 < PH, st1 = lane_on && t4 + 4 < PH;
+  uint32_t phase = 0;
+  for (;;) {
+    mbar_wait(&ctl->desc_full, phase);
+    const ItemSlot it = ctl->item;
+    if (it.kind == 2) break;
+    if (it.kind == 1) {
+      mbar_wait(&ctl->band_full, phase);
+      phase ^= 1;
+      const RoiGeom g = roi_geom(d, rois, levels, it.fb_roi, c.PH, c.PW, c.sr, c.finest);
+      gather_roi_chunk<false>(d, g, it.fb_roi, it.fb_c0, min(32, c.C - it.fb_c0), out, c.PH, c.PW, tid, Tc);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->band_empty);
+      continue;
+    }
+    // ids two RoIs ahead, tables one RoI ahead: no global latency between jobs
+    const int* list = w.list + it.lst;
+    int id0 = cw < it.cnt ? list[cw] : -1;
+    int id1 = cw + n_cwarps < it.cnt ? list[cw + n_cwarps] : -1;
+    uint2 ye = make_uint2(0u, 0u), xe = make_uint2(0u, 0u);
+    if (id0 >= 0) {
+      if (lane < TY) ye = w.tab[(size_t)id0 * ENT + lane];
+      xe = w.tab[(size_t)id0 * ENT + TY + xs];
+    }
+    mbar_wait(&ctl->band_full, phase);
+    phase ^= 1;
+    if (!it.bulk) {   // rows not 16-byte aligned: cooperative load by the consumers
+      const PlanLevel& v = c.lv[it.lvl];
+      const int chan_floats = it.chan_bytes >> 2;
+      const float* src0 = d.feat[it.lvl] + (((size_t)it.img * c.C + it.c0) * v.H + it.r0) * v.W;
+      for (int i = tid; i < it.ncur * chan_floats; i += Tc) {
+        const int j = i / chan_floats;
+        buf[i] = __ldg(src0 + (size_t)j * v.H * v.W + (i - j * chan_floats));
+      }
+      consumer_sync(Tc);
+    }
+    const int pitch_bytes = it.pitch_bytes;
+    for (int k = cw; k < it.cnt; k += n_cwarps) {
+      const int n = id0;
+      __syncwarp();                       // the previous job's reads of the slot are done
+      if (lane < TY) slot[lane] = ye;
+      const uint2 xc = xe;
+      __syncwarp();
+      {
+        const int q2 = k + 2 * n_cwarps;
+        const int id2 = q2 < it.cnt ? list[q2] : -1;
+        if (id1 >= 0) {
+          if (lane < TY) ye = w.tab[(size_t)id1 * ENT + lane];
+          xe = w.tab[(size_t)id1 * ENT + TY + xs];
+        }
+        id0 = id1; id1 = id2;
+      }
+      const float lx = __uint_as_float(xc.y);
+      const float wx = lane_on ? (odd ? lx : 1.0f - lx) * 0.25f : 0.0f;
+      const char* px = reinterpret_cast<const char*>(buf) + xc.x + (odd ? 4 : 0);
+      float* o = out + ((size_t)n * c.C + it.c0) * BINS;
+      for (int j = 0; j < it.ncur; ++j) {
+        float acc[8];
+#pragma unroll
+        for (int ph = 0; ph < PH; ++ph) {
+          const uint4 e = slot4[ph];      // samples 2ph, 2ph+1: {row offset, l} each
+          const char* r0 = px + e.x;
+          const char* r1 = px + e.z;
+          const float v00 = ldf(r0), v01 = ldf(r0 + pitch_bytes), v10 = ldf(r1), v11 = ldf(r1 + pitch_bytes);
+          const float a = fmaf(__uint_as_float(e.y), v01 - v00, v00);
+          const float b = fmaf(__uint_as_float(e.w), v11 - v10, v10);
+          acc[ph] = (a + b) * wx;
+        }
+#pragma unroll
+        for (int ph = PH; ph < 8; ++ph) acc[ph] = 0.0f;
+        // fold the 4 lanes of every bin; lane (pw, t) ends with bins ph = t and ph = t + 4
+        float r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float keep = odd ? acc[2 * q + 1] : acc[2 * q];
+          const float send = odd ? acc[2 * q] : acc[2 * q + 1];
+          r[q] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+        float s2[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float keep = up ? r[2 * q + 1] : r[2 * q];
+          const float send = up ? r[2 * q] : r[2 * q + 1];
+          s2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        if (st0) o[o0] = s2[0];
+        if (st1) o[o1] = s2[1];
+        px += it.chan_bytes;
+        o += BINS;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ctl->band_empty);
+  }
+}
+
 // --------------------------------------------------------------- backward --------
 // L2 RED.ADD throughput on B200 is bound per 32-byte SECTOR touched by a warp-level RED instruction
 // (~200 G sector-ops/s, profiles/microbench), not per lane, and shared-memory fp32 atomics are CAS
@@ -692,9 +829,11 @@ int plane_forward(const FpnDesc& d, const float* rois, const int* levels, float*
   MXD_REQUIRE(((uintptr_t)ws & 255) == 0, MXD_EINVAL, "workspace must be 256-byte aligned");
   int rc;
   if ((rc = run_planner(d, c, w, rois, levels, R, 0, st))) return rc;
-  auto kern = (sr == 2) ? roi_align_plane_fwd_kernel<2> : roi_align_plane_fwd_kernel<0>;
-  static int attr_done[2] = {0, 0};
-  const int ki = sr == 2 ? 0 : 1;
+  const bool tap = sr == 2 && PH == 7 && PW == 7 && c.tab_bytes >= ((c.threads - 32) >> 5) * 128;
+  auto kern = tap ? roi_align_plane_fwd_tap_kernel<7, 7>
+                  : (sr == 2) ? roi_align_plane_fwd_kernel<2> : roi_align_plane_fwd_kernel<0>;
+  static int attr_done[3] = {0, 0, 0};
+  const int ki = tap ? 2 : sr == 2 ? 0 : 1;
   if (attr_done[ki] < c.smem_bytes) {
     MXD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_done[ki] = kSmemLimit;
