@@ -27,6 +27,12 @@ constexpr int kSmemLimit = 227 * 1024;       // per-CTA opt-in maximum on sm_100
 constexpr int kBigRing = 14 * 1024;          // table area in one-CTA-per-SM mode: leaves 54400 floats = a 200x272 plane
 constexpr int kSmallRing = 8 * 1024;
 constexpr int kMiscBytes = 512;              // mbarrier + scalars + staged RoI ids
+// stream forward kernel (7x7 / sample_ratio 2): two band buffers + two table buffers per CTA
+constexpr int kS4TabBytes = 16 * 1024;       // one table buffer
+constexpr int kS4RoiEnt = 30;                // 28 tap entries + {RoI id, 0} + pad = 240 bytes (16-byte multiple)
+constexpr int kS4MaxRois = kS4TabBytes / (kS4RoiEnt * 8);
+constexpr int kS4KC = 4;                     // items (channel groups) per work unit
+constexpr int kS4CtlBytes = 512;
 
 struct PlanLevel {
   int H, W;
@@ -37,6 +43,8 @@ struct PlanLevel {
   int band_base;   // first band of this level inside one image's band table
   int item_base;   // first item id of this level
   int n_items;     // N * nbands * ncg
+  int nchunk;      // stream kernel: channel-group chunks per band (kS4KC items each)
+  int unit_base;   // stream kernel: first unit id of this level
 };
 
 struct PlanCfg {
@@ -45,6 +53,7 @@ struct PlanCfg {
   int bands_per_img, NB, n_plane_items;
   int budget_floats, chunk_rois, tab_bytes, slot_bytes;
   int threads, smem_bytes, ctas_per_sm, group;
+  int stream, n_units;
   float finest;
 };
 
@@ -58,6 +67,7 @@ struct PlanWs {
   int* list;     // [R] RoI ids grouped by band
   int* fb_list;  // [R] RoIs for the gather fallback
   uint2* tab;    // [R][ty+tx] packed {offset | hi_bit<<31, lo-weight bits}
+  uint2* tabg;   // [R][kS4RoiEnt] the same tables in band-grouped order + {RoI id, 0} (stream kernel)
   size_t bytes;
 };
 
@@ -74,15 +84,18 @@ static PlanWs carve_plan(void* base, int R, int NB, int entries) {
   w.list = (int*)take(sizeof(int) * (size_t)(R > 0 ? R : 1));
   w.fb_list = (int*)take(sizeof(int) * (size_t)(R > 0 ? R : 1));
   w.tab = (uint2*)take(sizeof(uint2) * (size_t)(R > 0 ? R : 1) * entries);
+  w.tabg = (uint2*)take(sizeof(uint2) * (size_t)(R > 0 ? R : 1) * kS4RoiEnt);
   w.bytes = off;
   return w;
 }
 
 // Host: choose bands / channel groups per level for the shared-memory budget.
 static bool make_cfg(int N, int C, int L, const int* Hs, const int* Ws, int PH, int PW, int sr, float finest,
-                     PlanCfg* c) {
+                     PlanCfg* c, bool stream = false) {
   if (sr <= 0 || PH * sr > 64 || PW * sr > 32) return false;   // adaptive / very fine sampling: gather kernels
+  if (stream && (sr != 2 || PH != 7 || PW != 7)) return false;
   memset(c, 0, sizeof(*c));
+  c->stream = stream ? 1 : 0;
   c->L = L; c->N = N; c->C = C; c->PH = PH; c->PW = PW; c->sr = sr; c->ty = PH * sr; c->tx = PW * sr;
   c->finest = finest;
   const int entry_bytes = (c->ty + c->tx) * (int)sizeof(uint2);
@@ -109,8 +122,14 @@ static bool make_cfg(int N, int C, int L, const int* Hs, const int* Ws, int PH, 
   c->slot_bytes = entry_bytes;
   if (2 * c->group < c->ty + c->tx) return false;   // a lane moves at most two table entries
   c->budget_floats = ((smem_cta - c->tab_bytes - kMiscBytes) / 4) & ~3;
+  if (stream) {
+    if (big) return false;                 // a plane that only fits whole: the one-CTA plane kernel keeps it resident
+    c->ctas_per_sm = 1; c->threads = 1024; c->tab_bytes = 2 * kS4TabBytes;
+    c->budget_floats = (((kSmemLimit - 2 * kS4TabBytes - kS4CtlBytes) / 2) / 4) & ~3;
+  }
   if (c->budget_floats < 4096) return false;
-  c->smem_bytes = c->budget_floats * 4 + c->tab_bytes + kMiscBytes;
+  c->smem_bytes = stream ? 2 * c->budget_floats * 4 + 2 * kS4TabBytes + kS4CtlBytes
+                         : c->budget_floats * 4 + c->tab_bytes + kMiscBytes;
   int band_base = 0, item_base = 0;
   for (int l = 0; l < L; ++l) {
     PlanLevel& v = c->lv[l];
@@ -132,6 +151,22 @@ static bool make_cfg(int N, int C, int L, const int* Hs, const int* Ws, int PH, 
     v.ncg = (C + v.cg - 1) / v.cg;
     v.band_base = band_base; band_base += v.nbands;
     v.item_base = item_base; v.n_items = N * v.nbands * v.ncg; item_base += v.n_items;
+    if (stream) {     // every level must be plane/band capable and loadable with 16-byte-granular bulk copies
+      if (v.band_rows == 0) return false;
+      if (v.nbands == 1) {          // whole planes: one contiguous copy per channel group
+        const size_t pb = (size_t)v.H * v.W * 4;
+        int al = 1;
+        while ((pb * al) & 15) al <<= 1;
+        if (v.cg < al || (C % al) != 0) return false;
+        v.cg = v.cg / al * al;
+        v.ncg = (C + v.cg - 1) / v.cg;
+        v.n_items = N * v.nbands * v.ncg;
+      } else if ((v.W & 3) != 0) {
+        return false;
+      }
+    }
+    v.nchunk = (v.ncg + kS4KC - 1) / kS4KC;
+    v.unit_base = c->n_units; c->n_units += N * v.nbands * v.nchunk;
   }
   c->bands_per_img = band_base;
   c->NB = N * band_base;
@@ -239,6 +274,19 @@ __global__ void __launch_bounds__(1024) plan_group_kernel(PlanCfg c, PlanWs w, i
     if (m < 0) continue;
     w.list[w.start[m] + atomicAdd(&w.cursor[m], 1)] = n;
   }
+}
+
+// Stream kernel: the tables in band-grouped order, so one bulk copy brings a band's RoIs to shared memory.
+__global__ void __launch_bounds__(256) plan_pack_kernel(PlanCfg c, PlanWs w, int R) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pos = i / kS4RoiEnt, e = i - pos * kS4RoiEnt;
+  const int ent = c.ty + c.tx;
+  if (pos >= R - w.hdr[1]) return;                // planned RoIs = all but the fallback ones
+  const int n = w.list[pos];
+  uint2 v = make_uint2(0u, 0u);
+  if (e < ent) v = w.tab[(size_t)n * ent + e];
+  else if (e == ent) v = make_uint2((unsigned)n, 0u);
+  w.tabg[(size_t)pos * kS4RoiEnt + e] = v;
 }
 
 __device__ __forceinline__ float ldf(const char* p) { return *reinterpret_cast<const float*>(p); }
@@ -609,6 +657,229 @@ roi_align_plane_fwd_tap_kernel(const __grid_constant__ FpnDesc d, const __grid_c
   }
 }
 
+// ------------------------------------- forward, 7x7 / sample_ratio 2, stream kernel ---
+// One CTA per SM: 31 consumer warps + one producer warp, TWO band buffers and two table buffers.
+// A work unit is (image, level, band, chunk of kS4KC channel groups); the producer lands the band's packed
+// RoI tables once per unit (one bulk copy from the band-grouped table) and then streams the unit's channel
+// planes through the two band buffers, so the next plane is in flight while the current one is pooled.
+// Consumer warps pull (RoI) jobs of the current buffer off a shared-memory counter: no warp waits for
+// another one inside a buffer, and a warp that finds the buffer drained moves on to the next.  Per job the
+// tap-lane scheme of roi_align_plane_fwd_tap_kernel applies; tables are read straight from the unit's
+// shared-memory copy (no per-job global traffic at all).
+struct S4Desc {
+  int kind;            // 0 band, 1 gather fallback, 2 stop
+  int first, last;     // first / last buffer of a table chunk: wait for / release the table buffer
+  int tb, cnt;         // table buffer, RoIs in it
+  int ncur, c0, chan_bytes, pitch_bytes;
+  int fb_roi, fb_c0, pad;
+};
+struct S4Ctl {
+  u64 full[2], empty[2], tfull[2], tempty[2];
+  int ctr[2];
+  int pad[2];
+  S4Desc desc[2];
+};
+static_assert(sizeof(S4Ctl) <= kS4CtlBytes, "control block");
+
+__device__ __forceinline__ void s4_producer(const FpnDesc& d, const PlanCfg& c, const PlanWs& w, S4Ctl* ctl,
+                                            unsigned char* smem, int lane) {
+  const int n_fb = w.hdr[1];
+  const int fb_chunks = (c.C + 31) / 32;
+  const int total = c.n_units + n_fb * fb_chunks;
+  const size_t buf_bytes = (size_t)c.budget_floats * 4;
+  uint32_t m = 0, u = 0;
+  auto publish = [&](const S4Desc& ds, const float* src0, size_t plane_sz) {
+    const int b = m & 1;
+    mbar_wait(&ctl->empty[b], ((m >> 1) & 1u) ^ 1u);
+    if (lane == 0) {
+      ctl->desc[b] = ds;
+      ctl->ctr[b] = 0;
+      if (ds.kind == 0) {
+        mbar_arrive_expect_tx(&ctl->full[b], (uint32_t)(ds.ncur * ds.chan_bytes));
+        if ((size_t)ds.chan_bytes == plane_sz * 4) {      // whole planes are contiguous: one copy
+          bulk_g2s(smem + b * buf_bytes, src0, (uint32_t)(ds.ncur * ds.chan_bytes), &ctl->full[b]);
+        } else {
+          for (int j = 0; j < ds.ncur; ++j)
+            bulk_g2s(smem + b * buf_bytes + (size_t)j * ds.chan_bytes, src0 + (size_t)j * plane_sz,
+                     (uint32_t)ds.chan_bytes, &ctl->full[b]);
+        }
+      } else {
+        mbar_arrive(&ctl->full[b]);
+      }
+    }
+    ++m;
+  };
+  for (;;) {
+    int unit = 0;
+    if (lane == 0) unit = atomicAdd(&w.hdr[0], 1);
+    unit = __shfl_sync(0xffffffffu, unit, 0);
+    if (unit >= total) break;
+    S4Desc ds;
+    ds.kind = 0; ds.first = ds.last = ds.tb = ds.cnt = ds.ncur = ds.c0 = ds.chan_bytes = ds.pitch_bytes = 0;
+    ds.fb_roi = ds.fb_c0 = ds.pad = 0;
+    if (unit >= c.n_units) {
+      const int f = unit - c.n_units;
+      ds.kind = 1; ds.fb_roi = w.fb_list[f / fb_chunks]; ds.fb_c0 = (f % fb_chunks) * 32;
+      publish(ds, nullptr, 0);
+      continue;
+    }
+    int l = 0;
+    while (l + 1 < c.L && unit >= c.lv[l + 1].unit_base) ++l;
+    const PlanLevel& v = c.lv[l];
+    int r = unit - v.unit_base;
+    const int chunk = r % v.nchunk; r /= v.nchunk;
+    const int band = r % v.nbands, img = r / v.nbands;
+    const int bidx = img * c.bands_per_img + v.band_base + band;
+    const int cnt = w.cnt[bidx];
+    if (cnt == 0) continue;
+    const int lst = w.start[bidx];
+    const int r0 = band * v.band_rows;
+    // whole-plane levels always load whole planes: one contiguous (and 16-byte aligned) copy per group
+    const int nrows = v.nbands == 1 ? v.H : min(w.rmax[bidx], v.H - 1) - r0 + 1;
+    const size_t plane_sz = (size_t)v.H * v.W;
+    const int i0 = chunk * kS4KC, i1 = min(v.ncg, i0 + kS4KC);
+    ds.chan_bytes = nrows * v.W * 4;
+    ds.pitch_bytes = v.W * 4;
+    for (int rc = 0; rc < cnt; rc += kS4MaxRois) {
+      const int nr = min(kS4MaxRois, cnt - rc);
+      const int tb = u & 1;
+      mbar_wait(&ctl->tempty[tb], ((u >> 1) & 1u) ^ 1u);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&ctl->tfull[tb], (uint32_t)(nr * kS4RoiEnt * 8));
+        bulk_g2s(smem + 2 * buf_bytes + (size_t)tb * kS4TabBytes, w.tabg + (size_t)(lst + rc) * kS4RoiEnt,
+                 (uint32_t)(nr * kS4RoiEnt * 8), &ctl->tfull[tb]);
+      }
+      ds.tb = tb; ds.cnt = nr;
+      for (int i = i0; i < i1; ++i) {
+        ds.first = i == i0; ds.last = i == i1 - 1;
+        ds.c0 = i * v.cg;
+        ds.ncur = min(v.cg, c.C - ds.c0);
+        publish(ds, d.feat[l] + (((size_t)img * c.C + ds.c0) * v.H + r0) * v.W, plane_sz);
+      }
+      ++u;
+    }
+  }
+  S4Desc ds;
+  ds.kind = 2; ds.first = ds.last = ds.tb = ds.cnt = ds.ncur = ds.c0 = ds.chan_bytes = ds.pitch_bytes = 0;
+  ds.fb_roi = ds.fb_c0 = ds.pad = 0;
+  publish(ds, nullptr, 0);
+}
+
+template <int PH, int PW>
+__global__ void __launch_bounds__(1024, 1)
+roi_align_stream_fwd_kernel(const __grid_constant__ FpnDesc d, const __grid_constant__ PlanCfg c, PlanWs w,
+                            const float* __restrict__ rois, const int* __restrict__ levels,
+                            float* __restrict__ out) {
+  static_assert(4 * PW <= 32 && PH <= 8, "lane = x tap, 8 accumulators");
+  constexpr int TY = 2 * PH, TX = 2 * PW, BINS = PH * PW;
+  static_assert(TY + TX + 1 <= kS4RoiEnt, "table entry layout");
+  extern __shared__ __align__(128) unsigned char smem[];
+  const size_t buf_bytes = (size_t)c.budget_floats * 4;
+  S4Ctl* ctl = reinterpret_cast<S4Ctl*>(smem + 2 * buf_bytes + 2 * kS4TabBytes);
+  const int tid = threadIdx.x;
+  const int Tc = blockDim.x - 32;
+  const int n_cwarps = Tc >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->full[i], 1);
+      mbar_init(&ctl->empty[i], n_cwarps);
+      mbar_init(&ctl->tfull[i], 1);
+      mbar_init(&ctl->tempty[i], n_cwarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid >= Tc) {
+    s4_producer(d, c, w, ctl, smem, tid - Tc);
+    return;
+  }
+  const int lane = tid & 31;
+  const int xs = min(lane >> 1, TX - 1);
+  const bool lane_on = lane < 2 * TX;
+  const int t4 = lane & 3, pw = min(lane >> 2, PW - 1);
+  const bool odd = lane & 1, up = lane & 2;
+  const int o0 = t4 * PW + pw, o1 = (t4 + 4) * PW + pw;
+  const bool st0 = lane_on && t4 < PH, st1 = lane_on && t4 + 4 < PH;
+  const int tap_off = odd ? 4 : 0;
+  uint32_t m = 0, u = 0;
+  for (;;) {
+    const int b = m & 1;
+    mbar_wait(&ctl->full[b], (m >> 1) & 1u);
+    const S4Desc* dp = &ctl->desc[b];
+    const int kind = dp->kind;
+    if (kind == 2) break;
+    if (kind == 1) {
+      const int fb_roi = dp->fb_roi, fb_c0 = dp->fb_c0;
+      const RoiGeom g = roi_geom(d, rois, levels, fb_roi, c.PH, c.PW, c.sr, c.finest);
+      gather_roi_chunk<false>(d, g, fb_roi, fb_c0, min(32, c.C - fb_c0), out, c.PH, c.PW, tid, Tc);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->empty[b]);
+      ++m;
+      continue;
+    }
+    const int tb = dp->tb, cnt = dp->cnt, ncur = dp->ncur, c0 = dp->c0;
+    const int chan_bytes = dp->chan_bytes, pitch_bytes = dp->pitch_bytes;
+    const bool first = dp->first, last = dp->last;
+    if (first) mbar_wait(&ctl->tfull[tb], (u >> 1) & 1u);
+    const unsigned char* tabs = smem + 2 * buf_bytes + (size_t)tb * kS4TabBytes;
+    const char* bufb = reinterpret_cast<const char*>(smem + b * buf_bytes) + tap_off;
+    for (;;) {
+      int k = 0;
+      if (lane == 0) k = atomicAdd(&ctl->ctr[b], 1);
+      k = __shfl_sync(0xffffffffu, k, 0);
+      if (k >= cnt) break;
+      const uint2* te = reinterpret_cast<const uint2*>(tabs + (size_t)k * (kS4RoiEnt * 8));
+      const uint4* y4 = reinterpret_cast<const uint4*>(te);
+      const int n = (int)te[TY + TX].x;
+      const uint2 xc = te[TY + xs];
+      const float lx = __uint_as_float(xc.y);
+      const float wx = lane_on ? (odd ? lx : 1.0f - lx) * 0.25f : 0.0f;
+      const char* px = bufb + xc.x;
+      float* o = out + ((size_t)n * c.C + c0) * BINS;
+      for (int j = 0; j < ncur; ++j) {
+        float acc[8];
+#pragma unroll
+        for (int ph = 0; ph < PH; ++ph) {
+          const uint4 e = y4[ph];         // samples 2ph, 2ph+1: {row offset, l} each
+          const char* r0 = px + e.x;
+          const char* r1 = px + e.z;
+          const float v00 = ldf(r0), v01 = ldf(r0 + pitch_bytes), v10 = ldf(r1), v11 = ldf(r1 + pitch_bytes);
+          const float a = fmaf(__uint_as_float(e.y), v01 - v00, v00);
+          const float bq = fmaf(__uint_as_float(e.w), v11 - v10, v10);
+          acc[ph] = (a + bq) * wx;
+        }
+#pragma unroll
+        for (int ph = PH; ph < 8; ++ph) acc[ph] = 0.0f;
+        float r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float keep = odd ? acc[2 * q + 1] : acc[2 * q];
+          const float send = odd ? acc[2 * q] : acc[2 * q + 1];
+          r[q] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+        float s2[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float keep = up ? r[2 * q + 1] : r[2 * q];
+          const float send = up ? r[2 * q] : r[2 * q + 1];
+          s2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        if (st0) o[o0] = s2[0];
+        if (st1) o[o1] = s2[1];
+        px += chan_bytes;
+        o += BINS;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (last) mbar_arrive(&ctl->tempty[tb]);
+      mbar_arrive(&ctl->empty[b]);
+    }
+    if (last) ++u;
+    ++m;
+  }
+}
+
 // --------------------------------------------------------------- backward --------
 // L2 RED.ADD throughput on B200 is bound per 32-byte SECTOR touched by a warp-level RED instruction
 // (~200 G sector-ops/s, profiles/microbench), not per lane, and shared-memory fp32 atomics are CAS
@@ -790,8 +1061,13 @@ namespace mxd {
 
 size_t plane_workspace_bytes(int R, int N, int L, const int* Hs, const int* Ws, int C, int PH, int PW, int sr) {
   PlanCfg c;
-  if (!make_cfg(N, C, L, Hs, Ws, PH, PW, sr, 56.0f, &c)) return 256;
-  return carve_plan(nullptr, R, c.NB, c.ty + c.tx).bytes;
+  size_t need = 256;
+  if (make_cfg(N, C, L, Hs, Ws, PH, PW, sr, 56.0f, &c)) need = carve_plan(nullptr, R, c.NB, c.ty + c.tx).bytes;
+  if (make_cfg(N, C, L, Hs, Ws, PH, PW, sr, 56.0f, &c, true)) {
+    const size_t b = carve_plan(nullptr, R, c.NB, c.ty + c.tx).bytes;
+    if (b > need) need = b;
+  }
+  return need;
 }
 
 static int num_sms() {
@@ -823,12 +1099,29 @@ int plane_forward(const FpnDesc& d, const float* rois, const int* levels, float*
   *handled = 0;
   PlanCfg c;
   if (R == 0 || d.C == 0) return MXD_OK;
-  if (!make_cfg(d.N, d.C, d.num_levels, d.H, d.W, PH, PW, sr, finest, &c)) return MXD_OK;
+  bool stream = make_cfg(d.N, d.C, d.num_levels, d.H, d.W, PH, PW, sr, finest, &c, true);
+  for (int l = 0; stream && l < d.num_levels; ++l)
+    if ((reinterpret_cast<uintptr_t>(d.feat[l]) & 15) != 0) stream = false;     // TMA source alignment
+  if (!stream && !make_cfg(d.N, d.C, d.num_levels, d.H, d.W, PH, PW, sr, finest, &c)) return MXD_OK;
   PlanWs w = carve_plan(ws, R, c.NB, c.ty + c.tx);
   MXD_REQUIRE(ws_bytes >= w.bytes, MXD_EWORKSPACE, "roi_align workspace %zu < %zu bytes", ws_bytes, w.bytes);
   MXD_REQUIRE(((uintptr_t)ws & 255) == 0, MXD_EINVAL, "workspace must be 256-byte aligned");
   int rc;
   if ((rc = run_planner(d, c, w, rois, levels, R, 0, st))) return rc;
+  if (stream) {
+    plan_pack_kernel<<<(R * kS4RoiEnt + 255) / 256, 256, 0, st>>>(c, w, R);
+    MXD_POST_LAUNCH("roi_align_plan_pack");
+    static bool attr4 = false;
+    if (!attr4) {
+      MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_stream_fwd_kernel<7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kSmemLimit));
+      attr4 = true;
+    }
+    roi_align_stream_fwd_kernel<7, 7><<<num_sms(), c.threads, c.smem_bytes, st>>>(d, c, w, rois, levels, out);
+    MXD_POST_LAUNCH("roi_align_stream_fwd");
+    *handled = 1;
+    return MXD_OK;
+  }
   const bool tap = sr == 2 && PH == 7 && PW == 7 && c.tab_bytes >= ((c.threads - 32) >> 5) * 128;
   auto kern = tap ? roi_align_plane_fwd_tap_kernel<7, 7>
                   : (sr == 2) ? roi_align_plane_fwd_kernel<2> : roi_align_plane_fwd_kernel<0>;
