@@ -21,7 +21,7 @@
 //  * each tile is written to HBM exactly once with plain coalesced stores (req=write needs no
 //    memset; req=add adds on the way out).
 //
-// RoIs that sample outside the image, are taller than 64 feature rows or have degenerate bins
+// RoIs that sample outside the image, are taller than 256 feature rows or span more than 64 tiles
 // take the generic RED path afterwards (gather_roi_chunk<true>) - they are rare.
 #include "roi_align.cuh"
 #include "ptx.cuh"
@@ -31,9 +31,9 @@ namespace mxd {
 constexpr int kTbWarps = 31;                       // consumer warps; warp w owns tile row w
 constexpr int kTbThreads = (kTbWarps + 1) * 32;    // + one producer warp
 constexpr int kTbStages = 9;
-constexpr int kTbMaxHf = 64;                       // rows of the dense per-RoI row table
+constexpr int kTbMaxHfCap = 256;                   // rows of the dense per-RoI row table: min(cap, tallest map)
 constexpr int kTbPix = 33;                         // words per tile pixel (32 channels + 1 pad)
-constexpr int kTbMaxTiles = 32;                    // tiles one RoI may intersect
+constexpr int kTbMaxTiles = 64;                    // tiles one RoI may intersect
 constexpr int kTbMaxTh = kTbWarps;
 constexpr int kTbMaxTw = 48;
 constexpr int kTbRowWords = (kTbMaxTw + 1) * kTbPix;   // fixed row pitch: 48 columns + the trash column
@@ -48,7 +48,7 @@ struct TCfg {
   TLevel lv[MXD_MAX_LEVELS];
   int L, N, C, PH, PW, sr, ty, tx, bins;
   int tiles_per_img, NT, ncg, n_items;
-  int stage_bytes, off_xt, off_rt, off_g, tile_bytes, smem_bytes, max_rows;
+  int stage_bytes, off_xt, off_rt, off_g, tile_bytes, smem_bytes, max_rows, max_hf;
   int accumulate;
   float finest, inv_count;
 };
@@ -61,12 +61,12 @@ struct TWs {
   int* fb_list;    // [R]
   int4* roihdr;    // [R][2]  {y0, Hf, x0, x1} {b, lvl, ok, ntiles}
   uint2* xtab;     // [R][tx] {column of the low tap (unclamped form), weight of the high tap}
-  uint4* rowtab;   // [R][kTbMaxHf][2]  {first bin | nbins<<8, w0..w6}
+  uint4* rowtab;   // [R][max_hf][2]  {first bin | nbins<<8, w0..w6}
   int* pairs;      // [R * kTbMaxTiles]
   size_t bytes;
 };
 
-static TWs carve_tile(void* base, int R, int NT, int tx) {
+static TWs carve_tile(void* base, int R, int NT, int tx, int max_hf) {
   TWs w;
   size_t off = 0;
   const size_t r1 = (size_t)(R > 0 ? R : 1);
@@ -78,7 +78,7 @@ static TWs carve_tile(void* base, int R, int NT, int tx) {
   w.fb_list = (int*)take(sizeof(int) * r1);
   w.roihdr = (int4*)take(sizeof(int4) * 2 * r1);
   w.xtab = (uint2*)take(sizeof(uint2) * r1 * tx);
-  w.rowtab = (uint4*)take(sizeof(uint4) * 2 * r1 * kTbMaxHf);
+  w.rowtab = (uint4*)take(sizeof(uint4) * 2 * r1 * max_hf);
   w.pairs = (int*)take(sizeof(int) * r1 * kTbMaxTiles);
   w.bytes = off;
   return w;
@@ -103,6 +103,7 @@ static bool make_tcfg(int N, int C, int L, const int* Hs, const int* Ws, int PH,
   for (int l = 0; l < L; ++l) {
     TLevel& v = c->lv[l];
     v.H = Hs[l]; v.W = Ws[l];
+    if (v.H > c->max_hf) c->max_hf = v.H < kTbMaxHfCap ? v.H : kTbMaxHfCap;
     v.ntx = (v.W + kTbMaxTw - 1) / kTbMaxTw;
     v.tw = (v.W + v.ntx - 1) / v.ntx;
     int th_cap = max_rows;
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(256) tplan_rois_kernel(FpnDesc d, TCfg c, TWs 
   const int x0 = __reduce_min_sync(full, xlo);
   const int x1 = __reduce_max_sync(full, lane < c.tx ? xlo + 1 : -1);
   const int Hf = y1 - y0 + 1;
-  ok = ok && Hf >= 1 && Hf <= kTbMaxHf && y0 >= 0 && x0 >= 0;
+  ok = ok && Hf >= 1 && Hf <= c.max_hf && y0 >= 0 && x0 >= 0;
   bool rows_ok = true;
   if (ok) {
     for (int i0 = 0; i0 < Hf; i0 += 32) {
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(256) tplan_rois_kernel(FpnDesc d, TCfg c, TWs 
       }
       if (i < Hf) {
         const int nph = pa < 0 ? 0 : pl - pa + 1;
-        uint4* rec = w.rowtab + ((size_t)n * kTbMaxHf + i) * 2;
+        uint4* rec = w.rowtab + ((size_t)n * c.max_hf + i) * 2;
         rec[0] = make_uint4((unsigned)(pa < 0 ? 0 : pa) | ((unsigned)nph << 8), __float_as_uint(wr[0]),
                             __float_as_uint(wr[1]), __float_as_uint(wr[2]));
         rec[1] = make_uint4(__float_as_uint(wr[3]), __float_as_uint(wr[4]), __float_as_uint(wr[5]),
@@ -344,7 +345,7 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
           const uint32_t rt_bytes = (uint32_t)((rb - ra + 1) * 32);
           mbar_arrive_expect_tx(&ctl->full[s], g_bytes + rt_bytes);
           bulk_g2s(st + c.off_g, gout + ((size_t)n * c.C + cg * 32) * c.bins, g_bytes, &ctl->full[s]);
-          bulk_g2s(st + c.off_rt + ra * 32, w.rowtab + ((size_t)n * kTbMaxHf + (ra + ty0 - y0)) * 2, rt_bytes,
+          bulk_g2s(st + c.off_rt + ra * 32, w.rowtab + ((size_t)n * c.max_hf + (ra + ty0 - y0)) * 2, rt_bytes,
                    &ctl->full[s]);
         }
         ++m;
@@ -526,7 +527,7 @@ __global__ void __launch_bounds__(256) tile_bwd_fallback_kernel(FpnDesc d, TCfg 
 size_t tile_bwd_workspace_bytes(int R, int N, int L, const int* Hs, const int* Ws, int C, int PH, int PW, int sr) {
   TCfg c;
   if (!make_tcfg(N, C, L, Hs, Ws, PH, PW, sr, 56.0f, 0, &c)) return 0;
-  return carve_tile(nullptr, R, c.NT, c.tx).bytes;
+  return carve_tile(nullptr, R, c.NT, c.tx, c.max_hf).bytes;
 }
 
 int tile_backward(const FpnDesc& d, const float* rois, const int* levels, const float* gout, int R, int PH, int PW,
@@ -536,7 +537,7 @@ int tile_backward(const FpnDesc& d, const float* rois, const int* levels, const 
   if (R == 0 || d.C == 0) return MXD_OK;
   if (!make_tcfg(d.N, d.C, d.num_levels, d.H, d.W, PH, PW, sr, finest, accumulate, &c)) return MXD_OK;
   if ((reinterpret_cast<uintptr_t>(gout) & 15) != 0) return MXD_OK;     // TMA source alignment
-  TWs w = carve_tile(ws, R, c.NT, c.tx);
+  TWs w = carve_tile(ws, R, c.NT, c.tx, c.max_hf);
   MXD_REQUIRE(ws_bytes >= w.bytes, MXD_EWORKSPACE, "roi_align workspace %zu < %zu bytes", ws_bytes, w.bytes);
   MXD_REQUIRE(((uintptr_t)ws & 255) == 0, MXD_EINVAL, "workspace must be 256-byte aligned");
   int sms = 0, dev = 0;
