@@ -43,7 +43,7 @@ struct PlanLevel {
   int band_base;   // first band of this level inside one image's band table
   int item_base;   // first item id of this level
   int n_items;     // N * nbands * ncg
-  int nchunk;      // stream kernel: channel-group chunks per band (kS4KC items each)
+  int kc, nchunk;  // stream kernel: items (channel groups) per work unit, chunks per band
   int unit_base;   // stream kernel: first unit id of this level
 };
 
@@ -158,14 +158,20 @@ static bool make_cfg(int N, int C, int L, const int* Hs, const int* Ws, int PH, 
         int al = 1;
         while ((pb * al) & 15) al <<= 1;
         if (v.cg < al || (C % al) != 0) return false;
+        if (v.cg > 8) v.cg = 8;     // keep work units of all levels comparable (dynamic scheduling tail)
         v.cg = v.cg / al * al;
+        if (v.cg < al) v.cg = al;
         v.ncg = (C + v.cg - 1) / v.cg;
         v.n_items = N * v.nbands * v.ncg;
       } else if ((v.W & 3) != 0) {
         return false;
       }
     }
-    v.nchunk = (v.ncg + kS4KC - 1) / kS4KC;
+    v.kc = kS4KC / v.cg > 1 ? kS4KC / v.cg : 1;
+    v.nchunk = (v.ncg + v.kc - 1) / v.kc;
+  }
+  for (int l = L - 1; l >= 0; --l) {      // unit ids: coarsest level first - its units carry the most RoIs
+    PlanLevel& v = c->lv[l];
     v.unit_base = c->n_units; c->n_units += N * v.nbands * v.nchunk;
   }
   c->bands_per_img = band_base;
@@ -693,7 +699,6 @@ __device__ __forceinline__ void s4_producer(const FpnDesc& d, const PlanCfg& c, 
     mbar_wait(&ctl->empty[b], ((m >> 1) & 1u) ^ 1u);
     if (lane == 0) {
       ctl->desc[b] = ds;
-      ctl->ctr[b] = 0;
       if (ds.kind == 0) {
         mbar_arrive_expect_tx(&ctl->full[b], (uint32_t)(ds.ncur * ds.chan_bytes));
         if ((size_t)ds.chan_bytes == plane_sz * 4) {      // whole planes are contiguous: one copy
@@ -723,8 +728,8 @@ __device__ __forceinline__ void s4_producer(const FpnDesc& d, const PlanCfg& c, 
       publish(ds, nullptr, 0);
       continue;
     }
-    int l = 0;
-    while (l + 1 < c.L && unit >= c.lv[l + 1].unit_base) ++l;
+    int l = c.L - 1;                      // unit_base decreases with the level index
+    while (l > 0 && unit >= c.lv[l - 1].unit_base) --l;
     const PlanLevel& v = c.lv[l];
     int r = unit - v.unit_base;
     const int chunk = r % v.nchunk; r /= v.nchunk;
@@ -737,7 +742,7 @@ __device__ __forceinline__ void s4_producer(const FpnDesc& d, const PlanCfg& c, 
     // whole-plane levels always load whole planes: one contiguous (and 16-byte aligned) copy per group
     const int nrows = v.nbands == 1 ? v.H : min(w.rmax[bidx], v.H - 1) - r0 + 1;
     const size_t plane_sz = (size_t)v.H * v.W;
-    const int i0 = chunk * kS4KC, i1 = min(v.ncg, i0 + kS4KC);
+    const int i0 = chunk * v.kc, i1 = min(v.ncg, i0 + v.kc);
     ds.chan_bytes = nrows * v.W * 4;
     ds.pitch_bytes = v.W * 4;
     for (int rc = 0; rc < cnt; rc += kS4MaxRois) {
@@ -793,7 +798,7 @@ roi_align_stream_fwd_kernel(const __grid_constant__ FpnDesc d, const __grid_cons
     s4_producer(d, c, w, ctl, smem, tid - Tc);
     return;
   }
-  const int lane = tid & 31;
+  const int lane = tid & 31, cw = tid >> 5;
   const int xs = min(lane >> 1, TX - 1);
   const bool lane_on = lane < 2 * TX;
   const int t4 = lane & 3, pw = min(lane >> 2, PW - 1);
@@ -823,11 +828,11 @@ roi_align_stream_fwd_kernel(const __grid_constant__ FpnDesc d, const __grid_cons
     if (first) mbar_wait(&ctl->tfull[tb], (u >> 1) & 1u);
     const unsigned char* tabs = smem + 2 * buf_bytes + (size_t)tb * kS4TabBytes;
     const char* bufb = reinterpret_cast<const char*>(smem + b * buf_bytes) + tap_off;
-    for (;;) {
-      int k = 0;
-      if (lane == 0) k = atomicAdd(&ctl->ctr[b], 1);
-      k = __shfl_sync(0xffffffffu, k, 0);
-      if (k >= cnt) break;
+    // jobs of a buffer are equal-sized: static round-robin, rotated per message so that the warps that get
+    // the extra job of a partial round change from buffer to buffer (no counter, no atomics)
+    int k0 = cw + (int)((m * 11u) % (uint32_t)n_cwarps);
+    if (k0 >= n_cwarps) k0 -= n_cwarps;
+    for (int k = k0; k < cnt; k += n_cwarps) {
       const uint2* te = reinterpret_cast<const uint2*>(tabs + (size_t)k * (kS4RoiEnt * 8));
       const uint4* y4 = reinterpret_cast<const uint4*>(te);
       const int n = (int)te[TY + TX].x;
