@@ -288,15 +288,21 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
     if (lane == 0) item = atomicAdd(&w.hdr[0], 1);
     item = __shfl_sync(full, item, 0);
     if (item >= c.n_items) break;
-    // item = ((b * ncg + cg) * tiles_per_img + t): all tiles of one (image, channel group) are neighbours,
-    // so the RoIs' grad_out slices are re-read from L2 while they are hot
-    const int t = item % c.tiles_per_img;
-    const int r = item / c.tiles_per_img;
-    const int cg = r % c.ncg, b = r / c.ncg;
-    int l = 0;
-    while (l + 1 < c.L && t >= c.lv[l + 1].tile_base) ++l;
+    // Items are level-major, coarsest level first (its tiles carry the most RoIs: heavy items early, light ones
+    // fill the tail); inside a level all tiles of one (image, channel group) are neighbours, so the RoIs'
+    // grad_out slices - every RoI lives on exactly one level - are re-read from L2 while they are hot.
+    int l = c.L - 1, rem = item;
+    for (;;) {
+      const int n_l = c.lv[l].nty * c.lv[l].ntx * c.N * c.ncg;
+      if (rem < n_l || l == 0) break;
+      rem -= n_l; --l;
+    }
     const TLevel& v = c.lv[l];
-    const int tl = t - v.tile_base;
+    const int tiles_l = v.nty * v.ntx;
+    const int tl = rem % tiles_l;
+    const int r = rem / tiles_l;
+    const int cg = r % c.ncg, b = r / c.ncg;
+    const int t = v.tile_base + tl;
     const int ty0 = (tl / v.ntx) * v.th, tx0 = (tl % v.ntx) * v.tw;
     const int tile_id = b * c.tiles_per_img + t;
     const int cnt = w.cnt[tile_id], start = w.start[tile_id];
