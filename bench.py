@@ -195,7 +195,15 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to STDOUT when the communicator is created; the contract is ONE json
+        # line on stdout, so fd 1 points at stderr until the first collective has run.
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            t0 = torch.zeros(1, device=dev); dist.all_reduce(t0); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     K, Wm = args.steps, max(args.warmup, 3)
     first_image = rank * IMGS_PER_GPU
     peak_gbs, peak_src = measured_peaks()

@@ -204,6 +204,20 @@ int mxd_rpn_proposals_stages(const mxd_rpn_config* cfg, int batch, const void* w
                              size_t workspace_bytes, DLTensor* idx, DLTensor* boxes,
                              DLTensor* keep, DLTensor* counts, void* stream);
 
+/* mx.nd.contrib.MultiProposal / Proposal of mxnet 1.3.0 (multi_proposal.cc/.cu; SURVEY.md 8(a) Spec H
+ * alt-mode; the call site would be mxdetection/models/rpn_heads, /root/reference/README.md:28).
+ * cls_prob (N,2A,H,W) f32 [foreground = channels A..2A-1], bbox_pred (N,4A,H,W), im_info (N,3)
+ * [height,width,scale] -> rois (N*post_n,5) [batch,x1,y1,x2,y2] and, when not NULL, scores (N*post_n,1);
+ * rows beyond the kept boxes repeat them cyclically as mxnet does.  base_anchors: host float[A*4]
+ * (utils::GenerateAnchors table).  rpn_pre_nms_top_n <= 0 = all (at most 8192 rows are sorted).      */
+size_t mxd_multi_proposal_workspace_bytes(int batch, int num_anchors, int feat_h, int feat_w,
+                                          int rpn_pre_nms_top_n, int rpn_post_nms_top_n);
+int mxd_multi_proposal(const DLTensor* cls_prob, const DLTensor* bbox_pred, const DLTensor* im_info,
+                       DLTensor* rois, DLTensor* scores, const float* base_anchors, int num_anchors,
+                       float feature_stride, int rpn_pre_nms_top_n, int rpn_post_nms_top_n,
+                       float threshold, float rpn_min_size, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

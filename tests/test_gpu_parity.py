@@ -499,6 +499,25 @@ def test_rpn_proposals_cfg2_full_size():
     assert np.all(props[:, :-1, 4] >= props[:, 1:, 4])           # sortedness of the truncated output
 
 
+@pytest.mark.parametrize("N_,H,W,pre,post,scales", [(2, 38, 50, 6000, 300, (4, 8, 16, 32)), (1, 25, 34, 1000, 50, (8, 16, 32)),
+                                                    (3, 7, 9, 200, 600, (2,))])
+def test_multi_proposal_mx_layout(N_, H, W, pre, post, scales):
+    """mx.nd.contrib.MultiProposal (NCHW in, cyclically padded rois out) vs the oracle: identical rows."""
+    from mxdetection_b200.models.rpn_heads import MultiProposal
+    rng = np.random.default_rng(N_ * 100 + H)
+    A = 3 * len(scales)
+    cls = (1.0 / (1.0 + np.exp(-rng.normal(-2, 2, (N_, 2 * A, H, W))))).astype(F)
+    cls = np.round(cls * 64) / 64                                   # many exact score ties
+    bbox = rng.normal(0, 0.4, (N_, 4 * A, H, W)).astype(F)
+    info = np.array([[H * 16 - 5.0, W * 16 - 9.0, 1.5], [H * 16 - 40.0, W * 16 - 1.0, 1.0], [H * 12.0, W * 16.0, 0.7]], F)[:N_]
+    kw = dict(rpn_pre_nms_top_n=pre, rpn_post_nms_top_n=post, threshold=0.7, rpn_min_size=16, scales=scales,
+              ratios=(0.5, 1, 2), feature_stride=16)
+    rois, sc = MultiProposal(T(cls.astype(F)), T(bbox), T(info), output_score=True, **kw)
+    rref, sref = oracle.multi_proposal(cls.astype(F), bbox, info, **kw)
+    assert np.array_equal(N(sc), sref)
+    assert np.abs(N(rois) - rref).max() <= 1e-5 and np.array_equal(N(rois)[:, 0], rref[:, 0])
+
+
 def test_pipeline_is_cuda_graph_capturable():
     """No allocation / sync inside the library: the whole proposal stage replays from a CUDA graph."""
     from mxdetection_b200.models.rpn_heads import RPNHead, ProposalConfig

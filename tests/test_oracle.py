@@ -221,3 +221,29 @@ def test_topk_stable_ties():
     s = np.array([.5, .9, .5, .9, .1, .5], F)
     assert oracle.topk_stable(s, 4).tolist() == [1, 3, 0, 2]
     assert oracle.topk_stable(s, 100).tolist() == [1, 3, 0, 2, 5, 4]
+
+
+def test_multi_proposal_oracle_hand_cases():
+    """MXNet MultiProposal restatement: anchor table (KAT-2), FilterBox growth + score -1, cyclic padding."""
+    import oracle
+    A = 9
+    H, W = 4, 5
+    cls = np.zeros((1, 2 * A, H, W), np.float32); bbox = np.zeros((1, 4 * A, H, W), np.float32)
+    cls[0, A + 4, 1, 2] = 0.9          # anchor (ratio 1, scale 16) at (h=1, w=2)
+    cls[0, A + 4, 1, 3] = 0.8          # its right neighbour: IoU of two 256-boxes shifted by 16 = 0.88 > 0.7
+    cls[0, A + 0, 3, 0] = 0.7
+    info = np.array([[H * 16.0, W * 16.0, 1.0]], np.float32)
+    rois, sc = oracle.multi_proposal(cls, bbox, info, rpn_pre_nms_top_n=12, rpn_post_nms_top_n=5, threshold=0.7,
+                                     rpn_min_size=16, scales=(8, 16, 32), ratios=(0.5, 1, 2), feature_stride=16)
+    base = oracle.generate_anchors_mx(16, (8, 16, 32), (0.5, 1, 2))
+    assert np.array_equal(base[0], [-84, -40, 99, 55]) and np.array_equal(base[4], [-120, -120, 135, 135])
+    # zero deltas: proposals are the clipped anchors; the 0.8 box is suppressed by the 0.9 box
+    top = rois[0]
+    assert top[0] == 0 and np.array_equal(top[1:], [0, 0, W * 16 - 1, H * 16 - 1]) and sc[0, 0] == np.float32(0.9)
+    assert not np.any(sc[:, 0] == np.float32(0.8))
+    nk = len(np.unique(rois, axis=0))
+    assert np.array_equal(rois[nk:], rois[:5 - nk]) or nk == 5          # cyclic repetition
+    # a map larger than the image: positions at / beyond int(h/stride) get score -1 and sort last
+    info2 = np.array([[2 * 16.0, W * 16.0, 1.0]], np.float32)
+    _, sc2 = oracle.multi_proposal(cls, bbox, info2, rpn_pre_nms_top_n=-1, rpn_post_nms_top_n=3, scales=(8, 16, 32))
+    assert sc2[0, 0] == np.float32(0.9) and not np.any(sc2[:, 0] == np.float32(0.7))
