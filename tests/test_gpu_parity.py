@@ -518,6 +518,63 @@ def test_multi_proposal_mx_layout(N_, H, W, pre, post, scales):
     assert np.abs(N(rois) - rref).max() <= 1e-5 and np.array_equal(N(rois)[:, 0], rref[:, 0])
 
 
+# ===================================================== SURVEY 8(f) next rows N1 / N2 / N4 ==
+def test_random_sampler_and_target_packing_n1():
+    from mxdetection_b200.core.bbox import MaxIoUAssigner, RandomSampler, pack_targets
+    rng = np.random.default_rng(41)
+    base = oracle.gen_base_anchors(8, [8], [0.5, 1, 2])
+    anchors = oracle.grid_anchors(base, 40, 56, 8)
+    gts = syn.gt_boxes(rng, 320, 448, 9)
+    a = MaxIoUAssigner(0.7, 0.3, 0.3).assign(T(anchors), T(gts))
+    ra, _, _ = oracle.max_iou_assign(anchors, gts, None, 0.7, 0.3, 0.3)
+    keys = rng.random(anchors.shape[0]).astype(F)
+    keys[::7] = keys[3]                                            # ties
+    for num, frac, ub in ((256, 0.5, -1), (64, 0.25, 3), (8, 0.5, 0)):
+        s = RandomSampler(num, frac, ub).sample(a.gt_inds, T(keys))
+        pos, neg = oracle.targets.random_sample(ra, keys, num, frac, ub)
+        gp = N(s.pos_inds); gn = N(s.neg_inds)
+        assert int(s.num_pos.item()) == len(pos) and int(s.num_neg.item()) == len(neg)
+        assert np.array_equal(gp[gp >= 0], pos) and np.array_equal(gn[gn >= 0], neg)
+        lab, lw, tgt, tw = pack_targets(T(anchors), a.gt_inds, T(gts), s)
+        rl, rlw, rt, rtw = oracle.targets.pack_targets(anchors, ra, gts, pos, neg)
+        assert np.array_equal(N(lab), rl) and np.array_equal(N(lw), rlw) and np.array_equal(N(tw), rtw)
+        assert np.abs(N(tgt) - rt).max() <= 1e-6
+
+
+def test_multiclass_nms_and_det_bboxes_n2():
+    from mxdetection_b200.models.bbox_heads import get_det_bboxes, multiclass_nms
+    rng = np.random.default_rng(5)
+    n, C = 300, 21
+    rois = np.concatenate([np.zeros((n, 1)), syn.gt_boxes(rng, 600, 800, n)], 1).astype(F)
+    logits = rng.normal(0, 2, (n, C)); logits[:, 0] += 2
+    score = (np.exp(logits) / np.exp(logits).sum(1, keepdims=True)).astype(F)
+    score = (np.round(score * 256) / 256).astype(F)               # exact ties across classes
+    for pred_cols in (4, 4 * C):
+        pred = rng.normal(0, 1.0, (n, pred_cols)).astype(F)
+        dets, labels, num = get_det_bboxes(T(rois), T(score), T(pred), (600, 800), 1.0, 0.05, 0.5, 100)
+        rd, rl = oracle.targets.get_det_bboxes(rois, score, pred, (600, 800), 1.0, 0.05, 0.5, 100)
+        k = int(num.item())
+        assert k == len(rl) and np.array_equal(N(labels)[:k], rl) and np.all(N(labels)[k:] == -1)
+        assert np.abs(N(dets)[:k] - rd).max() <= 1e-5 and np.array_equal(N(dets)[:k, 4], rd[:, 4])
+    d2, l2, n2 = multiclass_nms(T(rois[:, 1:]), T(score), 2.0, 0.5, 10)          # nothing passes the threshold
+    assert int(n2.item()) == 0 and np.all(N(l2) == -1)
+
+
+def test_mask_target_n4():
+    from mxdetection_b200.core.mask import mask_target
+    rng = np.random.default_rng(8)
+    G, H, W = 5, 96, 128
+    masks = np.zeros((G, H, W), np.uint8)
+    for g in range(G):
+        y, x = np.ogrid[:H, :W]
+        masks[g] = ((y - rng.uniform(20, 70)) ** 2 / rng.uniform(100, 900) + (x - rng.uniform(30, 100)) ** 2 / rng.uniform(100, 1600)) <= 1
+    props = syn.gt_boxes(rng, H, W, 40)
+    inds = rng.integers(0, G, 40)
+    got = N(mask_target(T(props), T(inds.astype(np.int64)), T(masks), 28))
+    ref = oracle.targets.mask_target(props, inds, masks, 28)
+    assert got.shape == (40, 28, 28) and np.mean(got != ref) <= 1e-3        # >= 0.5 boundary pixels may flip by 1 ulp
+
+
 def test_pipeline_is_cuda_graph_capturable():
     """No allocation / sync inside the library: the whole proposal stage replays from a CUDA graph."""
     from mxdetection_b200.models.rpn_heads import RPNHead, ProposalConfig

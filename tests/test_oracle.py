@@ -247,3 +247,25 @@ def test_multi_proposal_oracle_hand_cases():
     info2 = np.array([[2 * 16.0, W * 16.0, 1.0]], np.float32)
     _, sc2 = oracle.multi_proposal(cls, bbox, info2, rpn_pre_nms_top_n=-1, rpn_post_nms_top_n=3, scales=(8, 16, 32))
     assert sc2[0, 0] == np.float32(0.9) and not np.any(sc2[:, 0] == np.float32(0.7))
+
+
+def test_next_row_oracles_hand_cases():
+    """N1 sampling contract, N2 class-aware NMS, N4 mask target on hand-checkable inputs."""
+    import oracle
+    t = oracle.targets
+    assigned = np.array([0, 2, -1, 1, 0, 0, 3], np.int32)
+    keys = np.array([.5, .9, .99, .9, .1, .7, .2], np.float32)
+    pos, neg = t.random_sample(assigned, keys, num=4, pos_fraction=0.5)
+    assert pos.tolist() == [1, 3] and neg.tolist() == [5, 0]          # tie .9/.9 -> lower index first; ignore (-1) never sampled
+    pos, neg = t.random_sample(assigned, keys, num=6, pos_fraction=0.5, neg_pos_ub=0)
+    assert pos.tolist() == [1, 3, 6] and neg.tolist() == []
+    # two identical boxes of different classes both survive; the same class is suppressed
+    boxes = np.array([[0, 0, 9, 9], [0, 0, 9, 9], [50, 50, 60, 60]], np.float32)
+    scores = np.array([[.1, .8, .1], [.1, .7, .6], [.9, .04, .06]], np.float32)
+    dets, labels = t.multiclass_nms(boxes, scores, 0.05, 0.5, 10)
+    # score order: .8 (b0,c1) keep; .7 (b1,c1) same class, IoU 1 -> out; .6 (b1,c2) keep; .1 (b0,c2) -> out; .06 (b2,c2) keep
+    assert labels.tolist() == [0, 1, 1] and dets[:, 4].tolist() == [np.float32(.8), np.float32(.6), np.float32(.06)]
+    # mask target of a full mask is all ones, of an empty mask all zeros
+    m = np.stack([np.ones((20, 30), np.uint8), np.zeros((20, 30), np.uint8)])
+    mt = t.mask_target(np.array([[2, 2, 25, 17], [2, 2, 25, 17]], np.float32), [0, 1], m, 14)
+    assert mt[0].all() and not mt[1].any()
