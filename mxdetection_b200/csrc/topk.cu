@@ -12,11 +12,20 @@
 //                       (2) keys >= L are compacted (warp-aggregated) and sorted;
 //                       (3) if more than CAP keys pass (adversarial input) an exact
 //                           11-bit radix select narrows them to exactly k first.
+//
+// Segments longer than CAP (the 160 k-anchor FPN level) run on a thread-block CLUSTER of 8 CTAs: CTA r owns
+// the groups [r*G/8, (r+1)*G/8) and therefore a strided 1/8 of the scores, the group maxima are all-gathered
+// through distributed shared memory, every CTA derives the same bound L, compacts its own share, and the
+// survivors are funnelled into CTA 0 for the final sort (one CTA scanning 650 KB twice measured 138 us).
+#include <cooperative_groups.h>
 #include "internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace mxd {
 
 constexpr int kTopkThreads = 1024;
+constexpr int kTopkCluster = 8;
 constexpr int kCap = MXD_SORT_CAP;
 constexpr int kRadixBits = 11;
 constexpr int kRadixBins = 1 << kRadixBits;
@@ -95,14 +104,17 @@ __device__ u64 radix_select_kth(const float* __restrict__ sc, int estride, int n
   return prefix;  // select keys >= prefix (low unprocessed bits are zero)
 }
 
+template <bool CLUSTER>
 __global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __grid_constant__ TopkParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64* keys = reinterpret_cast<u64*>(smem_raw);  // kCap entries
+  u64* keys = reinterpret_cast<u64*>(smem_raw);  // kCap entries (+ kCap more in cluster launches: the funnel of CTA 0)
   __shared__ unsigned int s_hist[kRadixBins];
   __shared__ u64 s_state[4];
   __shared__ int s_count;
+  __shared__ int s_cnts[kTopkCluster];
 
-  const int s = blockIdx.x;
+  const int rank = CLUSTER ? (int)cg::this_cluster().block_rank() : 0;
+  const int s = CLUSTER ? blockIdx.x / kTopkCluster : blockIdx.x;
   const int b = s / p.num_levels, l = s - b * p.num_levels;
   const int n = p.n[l], k = p.k[l];
   const int es = p.elem_stride;
@@ -111,7 +123,101 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __g
   const int tid = threadIdx.x;
   int count;
 
-  if (n <= kCap) {
+  bool funnelled = false;
+  if (CLUSTER && n > kCap) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int G = (k <= 2048) ? 4096 : kCap;
+    const int gpc = G / kTopkCluster;            // groups owned by this CTA (512 or 1024)
+    const int rows = kTopkThreads / gpc;         // threads per group (2 or 1)
+    const int gl = tid % gpc, tr = tid / gpc;
+    const int nt = (n + G - 1) / G;              // elements of a group: i = t*G + rank*gpc + gl, t < nt
+    constexpr int U = 8;
+    // (1) maxima of my groups
+    u64 m = 0;
+    for (int t0 = tr; t0 < nt; t0 += rows * U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = (long long)(t0 + u * rows) * G + rank * gpc + gl;
+        v[u] = (t0 + u * rows < nt && i < n) ? sc[(size_t)i * es] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = (long long)(t0 + u * rows) * G + rank * gpc + gl;
+        const u64 key = (t0 + u * rows < nt && i < n) ? make_key(v[u], (int)i, n, vt) : 0ull;
+        m = key > m ? key : m;
+      }
+    }
+    u64* funnel = keys + kCap;                   // scratch here, the candidate funnel of CTA 0 later
+    funnel[tid] = m;
+    __syncthreads();
+    if (tr == 0) {
+      for (int r = 1; r < rows; ++r) { const u64 o = funnel[r * gpc + gl]; m = o > m ? o : m; }
+      for (int dst = 0; dst < kTopkCluster; ++dst)       // all-gather: every CTA gets all G maxima
+        cluster.map_shared_rank(keys, dst)[rank * gpc + gl] = m;
+    }
+    cluster.sync();
+    bitonic_sort_desc(keys, G);
+    u64 L = keys[k - 1];
+    if (tid == 0) s_count = 0;
+    __syncthreads();  // everyone has read L before keys[] is overwritten
+    if (L == 0) L = 1;
+    // (2) compaction of my share
+    const unsigned lane = tid & 31;
+    for (int t0 = tr; t0 < nt; t0 += rows * U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = (long long)(t0 + u * rows) * G + rank * gpc + gl;
+        v[u] = (t0 + u * rows < nt && i < n) ? sc[(size_t)i * es] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = (long long)(t0 + u * rows) * G + rank * gpc + gl;
+        const u64 key = (t0 + u * rows < nt && i < n) ? make_key(v[u], (int)i, n, vt) : 0ull;
+        const bool take = key >= L;
+        const unsigned bal = __ballot_sync(0xffffffffu, take);
+        if (bal) {
+          const int leader = __ffs(bal) - 1;
+          int b0 = 0;
+          if ((int)lane == leader) b0 = atomicAdd(&s_count, __popc(bal));
+          b0 = __shfl_sync(0xffffffffu, b0, leader);
+          const int pos = b0 + __popc(bal & ((1u << lane) - 1u));
+          if (take && pos < kCap) keys[pos] = key;
+        }
+      }
+    }
+    __syncthreads();
+    const int mine = s_count;
+    if (tid == 0) cluster.map_shared_rank(s_cnts, 0)[rank] = mine;
+    cluster.sync();
+    int off = 0, total = 0;
+    {
+      const int* c0 = cluster.map_shared_rank(s_cnts, 0);
+      for (int q = 0; q < kTopkCluster; ++q) {
+        const int cq = c0[q];
+        if (q < rank) off += cq;
+        total += cq;
+      }
+    }
+    if (total <= kCap) {          // (3) funnel the survivors into CTA 0
+      u64* f0 = cluster.map_shared_rank(funnel, 0);
+      for (int j = tid; j < mine; j += kTopkThreads) f0[off + j] = keys[j];
+      cluster.sync();
+      if (rank != 0) return;
+      keys = funnel;
+      count = total;
+      funnelled = true;
+    } else {                      // adversarial input: CTA 0 redoes the segment with the exact radix path
+      cluster.sync();             // nobody leaves while its shared memory may still be read
+      if (rank != 0) return;
+    }
+  } else if (rank != 0) {
+    return;                       // short segment of a cluster launch: CTA 0 sorts it alone
+  }
+  if (funnelled) {
+    // count / keys are set
+  } else if (n <= kCap) {
     for (int i = tid; i < n; i += kTopkThreads) keys[i] = make_key(sc[(size_t)i * es], i, n, vt);
     count = n;
   } else {
@@ -260,13 +366,27 @@ int launch_topk(const TopkParams& p, cudaStream_t st) {
     MXD_REQUIRE(p.k[l] <= kCap, MXD_ENOTSUP, "top-k of %d rows exceeds the in-CTA sort capacity %d", p.k[l], kCap);
     MXD_REQUIRE(p.k[l] <= p.kmax && p.n[l] >= 0, MXD_EINVAL, "bad top-k geometry");
   }
+  bool big = false;
+  for (int l = 0; l < p.num_levels; ++l) big = big || p.n[l] > kCap;
   static bool attr_set = false;
   const int smem = kCap * (int)sizeof(u64);
   if (!attr_set) {
-    MXD_CUDA_OK(cudaFuncSetAttribute(topk_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MXD_CUDA_OK(cudaFuncSetAttribute(topk_segment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MXD_CUDA_OK(cudaFuncSetAttribute(topk_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * smem));
     attr_set = true;
   }
-  topk_segment_kernel<<<S, kTopkThreads, smem, st>>>(p);
+  if (big && (long long)S * kTopkCluster < (1ll << 31)) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(S * kTopkCluster)); cfg.blockDim = dim3(kTopkThreads);
+    cfg.dynamicSmemBytes = 2 * smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kTopkCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    MXD_CUDA_OK(cudaLaunchKernelEx(&cfg, topk_segment_kernel<true>, p));
+  } else {
+    topk_segment_kernel<false><<<S, kTopkThreads, smem, st>>>(p);
+  }
   MXD_POST_LAUNCH("topk_segment");
   return MXD_OK;
 }
