@@ -76,7 +76,10 @@ __device__ __forceinline__ float4 decode_box(float4 r, float4 dl, const float* m
   return o;
 }
 
-// Block-wide bitonic sort of P (power of two) u64 keys in shared memory, DESCENDING.
+// Block-wide bitonic sort of P (power of two) u64 keys in shared memory, DESCENDING.  Thread t owns the pairs
+// t, t + blockDim, ...; for strides <= 32 all pairs of a warp stay inside 64-key blocks that only this warp
+// touches, so those passes (6 of every merge stage) need a warp barrier only - 21 block barriers instead of
+// 78 for 4096 keys.  blockDim.x must be a multiple of 32.
 __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int P) {
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -87,9 +90,11 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int 
         const unsigned long long a = keys[lo], b = keys[hi];
         if ((a < b) == up) { keys[lo] = b; keys[hi] = a; }
       }
-      __syncthreads();
+      if (stride > 32 || (stride == 1 && size >= 64)) __syncthreads();   // the next pass (stride = size, other warps) needs a block barrier
+      else __syncwarp();
     }
   }
+  __syncthreads();
 }
 
 __device__ __forceinline__ int next_pow2(int v) {

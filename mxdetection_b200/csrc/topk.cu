@@ -38,6 +38,85 @@ __device__ __forceinline__ u64 make_key(float s, int i, int n, float valid_thres
   return ((u64)f32_orderable(s) << 32) | (u64)(uint32_t)(n - 1 - i);
 }
 
+// Warp 0 walks the 2048-bin histogram from the top and records the bin that holds the need-th largest key:
+// s_state = {bin, keys still needed inside it, keys in it}.
+__device__ __forceinline__ void radix_find_bin(const unsigned int* hist, int need, u64* s_state) {
+  if (threadIdx.x < 32) {
+    // lane L owns bins [hi-63, hi] with hi = 2047 - 64*L (descending walk)
+    const int lane = threadIdx.x;
+    const int hi = kRadixBins - 1 - 64 * lane;
+    unsigned sum = 0;
+    for (int b = 0; b < 64; ++b) sum += hist[hi - b];
+    unsigned incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned excl = incl - sum;
+    if (excl < (unsigned)need && incl >= (unsigned)need) {
+      unsigned run = excl;
+      for (int b = 0; b < 64; ++b) {
+        unsigned h = hist[hi - b];
+        if (run + h >= (unsigned)need) {
+          s_state[0] = (u64)(hi - b);
+          s_state[1] = (u64)(need - run);   // still needed inside this bin
+          s_state[2] = (u64)h;
+          break;
+        }
+        run += h;
+      }
+    }
+  }
+}
+
+// k-th largest of cnt DISTINCT non-zero 64-bit keys held in shared memory (1 <= k <= cnt): MSB-first 11-bit
+// radix passes over a shared-memory histogram.  Far fewer instructions than sorting when only the threshold is
+// needed (a 4096-key bitonic sort costs ~4 k instructions per warp).  Returns T: exactly k keys are >= T.
+__device__ u64 radix_select_smem(const u64* src, int cnt, int k, unsigned int* hist, u64* s_state) {
+  u64 prefix = 0, pmask = 0;
+  int need = k;
+  int pos = 64;
+  while (pos > 0) {
+    const int width = pos < kRadixBits ? pos : kRadixBits;
+    const int shift = pos - width;
+    const u64 dmask = (1ull << width) - 1;
+    for (int i = threadIdx.x; i < kRadixBins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const u64 key = src[i];
+      if (key != 0 && (key & pmask) == prefix) atomicAdd(&hist[(unsigned)((key >> shift) & dmask)], 1u);
+    }
+    __syncthreads();
+    radix_find_bin(hist, need, s_state);
+    __syncthreads();
+    const u64 digit = s_state[0];
+    need = (int)s_state[1];
+    const int binsz = (int)s_state[2];
+    prefix |= digit << shift;
+    pmask |= dmask << shift;
+    pos = shift;
+    __syncthreads();
+    if (binsz == need) break;  // the whole bin is selected
+  }
+  return prefix;
+}
+
+// Lower bound on the k-th largest key of the segment: the k-th largest of the G group maxima (every group
+// maximum is a key of the segment, so at least k keys are >= it).  Fewer than k non-zero maxima: take every
+// valid key (bound 1).
+__device__ u64 select_bound(const u64* maxima, int G, int k, unsigned int* hist, u64* s_state) {
+  __shared__ int s_nz;
+  if (threadIdx.x == 0) s_nz = 0;
+  __syncthreads();
+  int nz = 0;
+  for (int i = threadIdx.x; i < G; i += blockDim.x) nz += maxima[i] != 0;
+  nz = __reduce_add_sync(0xffffffffu, nz);
+  if ((threadIdx.x & 31) == 0 && nz) atomicAdd(&s_nz, nz);
+  __syncthreads();
+  if (s_nz < k) return 1ull;
+  return radix_select_smem(maxima, G, k, hist, s_state);
+}
+
 // Exact selection of the k-th largest key by MSB-first radix passes (slow path).
 __device__ u64 radix_select_kth(const float* __restrict__ sc, int estride, int n, int k, float vt,
                                 unsigned int* hist, u64* s_state) {
@@ -65,32 +144,7 @@ __device__ u64 radix_select_kth(const float* __restrict__ sc, int estride, int n
       if (key != 0 && (key & pmask) == prefix) atomicAdd(&hist[(unsigned)((key >> shift) & dmask)], 1u);
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-      // lane L owns bins [hi-63, hi] with hi = 2047 - 64*L (descending walk)
-      const int lane = threadIdx.x;
-      const int hi = kRadixBins - 1 - 64 * lane;
-      unsigned sum = 0;
-      for (int b = 0; b < 64; ++b) sum += hist[hi - b];
-      unsigned incl = sum;
-      for (int o = 1; o < 32; o <<= 1) {
-        unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      const unsigned excl = incl - sum;
-      if (excl < (unsigned)need && incl >= (unsigned)need) {
-        unsigned run = excl;
-        for (int b = 0; b < 64; ++b) {
-          unsigned h = hist[hi - b];
-          if (run + h >= (unsigned)need) {
-            s_state[0] = (u64)(hi - b);
-            s_state[1] = (u64)(need - run);   // still needed inside this bin
-            s_state[2] = (u64)h;
-            break;
-          }
-          run += h;
-        }
-      }
-    }
+    radix_find_bin(hist, need, s_state);
     __syncthreads();
     const u64 digit = s_state[0];
     need = (int)s_state[1];
@@ -157,11 +211,9 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __g
         cluster.map_shared_rank(keys, dst)[rank * gpc + gl] = m;
     }
     cluster.sync();
-    bitonic_sort_desc(keys, G);
-    u64 L = keys[k - 1];
+    u64 L = select_bound(keys, G, k, s_hist, s_state);
     if (tid == 0) s_count = 0;
-    __syncthreads();  // everyone has read L before keys[] is overwritten
-    if (L == 0) L = 1;
+    __syncthreads();  // everyone is done with the maxima before keys[] is overwritten
     // (2) compaction of my share
     const unsigned lane = tid & 31;
     for (int t0 = tr; t0 < nt; t0 += rows * U) {
@@ -252,11 +304,9 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __g
       }
     }
     __syncthreads();
-    bitonic_sort_desc(keys, G);
-    u64 L = keys[k - 1];
+    u64 L = select_bound(keys, G, k, s_hist, s_state);
     if (tid == 0) s_count = 0;
-    __syncthreads();  // everyone has read L before keys[] is overwritten
-    if (L == 0) L = 1;  // fewer than k valid rows: take every valid key
+    __syncthreads();  // everyone is done with the maxima before keys[] is overwritten
     // (2) compaction of keys >= L
     const int iters = (n + kTopkThreads - 1) / kTopkThreads;
     const unsigned lane = tid & 31;
@@ -305,6 +355,38 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __g
       }
       __syncthreads();
       count = min(s_count, kCap);
+    }
+  }
+  if (count > k) {
+    // only the top k are emitted: find their threshold with radix passes and sort k keys instead of `count`
+    // (non-zero keys only: zeros are dropped rows and sort last anyway)
+    __syncthreads();
+    int nzl = 0;
+    for (int i = tid; i < count; i += kTopkThreads) nzl += keys[i] != 0;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    nzl = __reduce_add_sync(0xffffffffu, nzl);
+    if ((tid & 31) == 0 && nzl) atomicAdd(&s_count, nzl);
+    __syncthreads();
+    const int nzc = s_count;
+    __syncthreads();
+    if (nzc > k) {
+      const u64 T = radix_select_smem(keys, count, k, s_hist, s_state);
+      u64 mine[kCap / kTopkThreads];
+      int nm = 0;
+#pragma unroll
+      for (int u = 0; u < kCap / kTopkThreads; ++u) {
+        const int i = u * kTopkThreads + tid;
+        mine[u] = (i < count) ? keys[i] : 0ull;
+      }
+      if (tid == 0) s_count = 0;
+      __syncthreads();          // every candidate is in registers: the array can be rewritten in place
+#pragma unroll
+      for (int u = 0; u < kCap / kTopkThreads; ++u)
+        if (mine[u] >= T && mine[u] != 0) keys[atomicAdd(&s_count, 1)] = mine[u];
+      (void)nm;
+      __syncthreads();
+      count = s_count;          // == k
     }
   }
   const int P = max(next_pow2(count), 2);
