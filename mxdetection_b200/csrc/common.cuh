@@ -108,6 +108,25 @@ __device__ __forceinline__ bool box_iou_pos(const float4& a, float area_a, const
   return true;
 }
 
+// Exactly `box_iou_pos(...) && iou > thr` (Spec B's strict test on the ROUNDED fp32 quotient) without the IEEE
+// division for all but borderline pairs: with p = fl(thr*union), inter > p*(1+3e-7) implies the real quotient
+// exceeds thr by more than one ulp (so its rounding is > thr) and inter < p*(1-3e-7) implies it is below thr (so
+// its rounding is <= thr); only the sliver in between pays for __fdiv_rn.
+__device__ __forceinline__ bool box_iou_gt(const float4& a, float area_a, const float4& b, float area_b, float d,
+                                           float thr) {
+  const float iw = __fadd_rn(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), d);
+  const float ih = __fadd_rn(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), d);
+  if (!(iw > 0.0f) || !(ih > 0.0f)) return false;
+  const float inter = __fmul_rn(iw, ih);
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  if (thr > 0.0f && uni > 0.0f && uni < 3.0e38f) {
+    const float p = __fmul_rn(thr, uni);
+    if (inter > __fmul_rn(p, 1.00000036f)) return true;
+    if (inter < __fmul_rn(p, 0.99999964f)) return false;
+  }
+  return __fdiv_rn(inter, uni) > thr;
+}
+
 // Correctly rounded fp32 exp/log (fp64 evaluation, one rounding) - Spec F.
 __device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
 __device__ __forceinline__ float log_cr(float x) { return (float)log((double)x); }

@@ -46,8 +46,7 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(NmsSortedArgs a, int W) {
   const int start = (cb == rb) ? t + 1 : 0;  // strictly later boxes only
   for (int i = start; i < ncol; ++i) {
     if (sid[i] != myid) continue;
-    float iou;
-    if (box_iou_pos(me, area, sb[i], sa[i], a.delta, &iou) && iou > a.thr) bits |= 1ull << i;
+    if (box_iou_gt(me, area, sb[i], sa[i], a.delta, a.thr)) bits |= 1ull << i;
   }
   a.mask[((size_t)s * a.n_max + r) * W + cb] = bits;
 }
