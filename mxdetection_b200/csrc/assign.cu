@@ -47,13 +47,14 @@ constexpr int kAnchorsPerThread = 4;
 
 __global__ void __launch_bounds__(kAssignThreads) assign_pass1_kernel(AssignArgs a) {
   __shared__ float4 s_gt[kGtChunk];
+  __shared__ float4 s_rej[kGtChunk];     // GT box grown by delta + 1: an anchor entirely outside it cannot intersect
   __shared__ float s_area[kGtChunk];
   __shared__ unsigned int s_max[kGtChunk];
   constexpr int A = kAnchorsPerThread;
   const int b = blockIdx.y;
   const int n0 = blockIdx.x * (kAssignThreads * A) + threadIdx.x;
   const int G = a.num_gts ? min(max(a.num_gts[b], 0), a.G) : a.G;
-  bool in[A], act[A];
+  bool in[A], act[A], posa[A];
   float4 me[A];
   float area[A], best[A];
   int arg[A];
@@ -69,7 +70,10 @@ __global__ void __launch_bounds__(kAssignThreads) assign_pass1_kernel(AssignArgs
       me[q] = a.anchors[n];
       area[q] = box_area_raw(me[q].x, me[q].y, me[q].z, me[q].w, a.delta);
     }
-    best[q] = -INFINITY;
+    posa[q] = area[q] > 0.0f;
+    // a rejected pair has IoU +0 (both areas positive): start from "GT 0 with IoU 0", which is what the
+    // first iteration of the exact loop would leave behind; degenerate anchors keep the exact -inf start
+    best[q] = (posa[q] && G > 0) ? 0.0f : -INFINITY;
     arg[q] = 0;
   }
   for (int g0 = 0; g0 < G; g0 += kGtChunk) {
@@ -78,13 +82,26 @@ __global__ void __launch_bounds__(kAssignThreads) assign_pass1_kernel(AssignArgs
     for (int i = threadIdx.x; i < gc; i += kAssignThreads) {
       const float4 g = a.gts[(size_t)b * a.G + g0 + i];
       s_gt[i] = g;
-      s_area[i] = box_area_raw(g.x, g.y, g.z, g.w, a.delta);
+      const float ga = box_area_raw(g.x, g.y, g.z, g.w, a.delta);
+      s_area[i] = ga;
       s_max[i] = 0u;
+      // quick-reject window (margin delta + 1 dwarfs every rounding of the exact test); a GT with a
+      // non-positive area rejects nothing, so 0/0 cases still reach the exact expression
+      const float mg = __fadd_rn(a.delta, 1.0f);
+      s_rej[i] = (ga > 0.0f) ? make_float4(__fsub_rn(g.x, mg), __fsub_rn(g.y, mg), __fadd_rn(g.z, mg), __fadd_rn(g.w, mg))
+                             : make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY);
     }
     __syncthreads();
     for (int i = 0; i < gc; ++i) {
       // Most (anchor, GT) pairs do not intersect: their IoU is +0 without the IEEE division (when the
-      // union is positive), cannot raise gt_max, and the warp skips the REDUX / atomic altogether.
+      // union is positive) and cannot raise gt_max.  Four compares per anchor prove it for a whole warp
+      // (128 anchors) at a time; only warps with a possible intersection run the exact expression.
+      const float4 rj = s_rej[i];
+      bool maybe = false;
+#pragma unroll
+      for (int q = 0; q < A; ++q)
+        maybe = maybe || (act[q] && (!posa[q] || !(me[q].z < rj.x || me[q].x > rj.z || me[q].w < rj.y || me[q].y > rj.w)));
+      if (!__any_sync(0xffffffffu, maybe)) continue;
       const float4 g = s_gt[i];
       const float ga = s_area[i];
       unsigned bits = 0u;
@@ -132,6 +149,7 @@ __global__ void __launch_bounds__(kAssignThreads) assign_pass2_kernel(AssignArgs
   __shared__ float4 s_gt[kGtChunk];
   __shared__ float s_area[kGtChunk];
   __shared__ float s_gtmax[kGtChunk];
+  __shared__ unsigned int s_gmin;        // bit image of the smallest qualifying gt_max of the chunk
   const int b = blockIdx.y;
   const int n = blockIdx.x * kAssignThreads + threadIdx.x;
   const int G = a.num_gts ? min(max(a.num_gts[b], 0), a.G) : a.G;
@@ -154,14 +172,19 @@ __global__ void __launch_bounds__(kAssignThreads) assign_pass2_kernel(AssignArgs
   for (int g0 = 0; g0 < G; g0 += kGtChunk) {
     const int gc = min(kGtChunk, G - g0);
     __syncthreads();
+    if (threadIdx.x == 0) s_gmin = 0x7f800000u;
+    __syncthreads();
     for (int i = threadIdx.x; i < gc; i += kAssignThreads) {
       const float4 g = a.gts[(size_t)b * a.G + g0 + i];
       s_gt[i] = g;
       s_area[i] = box_area_raw(g.x, g.y, g.z, g.w, a.delta);
-      s_gtmax[i] = __uint_as_float(a.gt_max[(size_t)b * a.G + g0 + i]);
+      const float gm = __uint_as_float(a.gt_max[(size_t)b * a.G + g0 + i]);
+      s_gtmax[i] = gm;
+      if (gm >= a.min_pos) atomicMin(&s_gmin, __float_as_uint(fmaxf(gm, 0.0f)));   // gt_max >= 0: uint order = float order
     }
     __syncthreads();
-    if (act) {
+    // an anchor whose own maximum is below every qualifying gt_max cannot tie with any of them
+    if (act && !(best < __uint_as_float(s_gmin))) {
       for (int i = 0; i < gc; ++i) {
         const float gm = s_gtmax[i];
         if (!(gm >= a.min_pos)) continue;
