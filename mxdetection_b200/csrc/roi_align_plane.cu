@@ -672,18 +672,15 @@ roi_align_plane_fwd_tap_kernel(const __grid_constant__ FpnDesc d, const __grid_c
 // another one inside a buffer, and a warp that finds the buffer drained moves on to the next.  Per job the
 // tap-lane scheme of roi_align_plane_fwd_tap_kernel applies; tables are read straight from the unit's
 // shared-memory copy (no per-job global traffic at all).
-struct S4Desc {
-  int kind;            // 0 band, 1 gather fallback, 2 stop
-  int first, last;     // first / last buffer of a table chunk: wait for / release the table buffer
-  int tb, cnt;         // table buffer, RoIs in it
-  int ncur, c0, chan_bytes, pitch_bytes;
-  int fb_roi, fb_c0, pad;
+struct S4Desc {       // 32 bytes: read with two LDS.128
+  int kind;            // 0 band, 1 gather fallback, 2 stop | first << 8 | last << 9 | table buffer << 10
+  int cnt;             // RoIs in the table buffer            (fallback: RoI id)
+  int ncur, c0;        // channels in the band buffer, first  (fallback: -, first channel)
+  int chan_bytes, pitch_bytes, pad0, pad1;
 };
 struct S4Ctl {
   u64 full[2], empty[2], tfull[2], tempty[2];
-  int ctr[2];
-  int pad[2];
-  S4Desc desc[2];
+  S4Desc desc[2];      // 16-byte aligned: 64 bytes of barriers precede
 };
 static_assert(sizeof(S4Ctl) <= kS4CtlBytes, "control block");
 
@@ -699,7 +696,7 @@ __device__ __forceinline__ void s4_producer(const FpnDesc& d, const PlanCfg& c, 
     mbar_wait(&ctl->empty[b], ((m >> 1) & 1u) ^ 1u);
     if (lane == 0) {
       ctl->desc[b] = ds;
-      if (ds.kind == 0) {
+      if ((ds.kind & 0xff) == 0) {
         mbar_arrive_expect_tx(&ctl->full[b], (uint32_t)(ds.ncur * ds.chan_bytes));
         if ((size_t)ds.chan_bytes == plane_sz * 4) {      // whole planes are contiguous: one copy
           bulk_g2s(smem + b * buf_bytes, src0, (uint32_t)(ds.ncur * ds.chan_bytes), &ctl->full[b]);
@@ -720,11 +717,10 @@ __device__ __forceinline__ void s4_producer(const FpnDesc& d, const PlanCfg& c, 
     unit = __shfl_sync(0xffffffffu, unit, 0);
     if (unit >= total) break;
     S4Desc ds;
-    ds.kind = 0; ds.first = ds.last = ds.tb = ds.cnt = ds.ncur = ds.c0 = ds.chan_bytes = ds.pitch_bytes = 0;
-    ds.fb_roi = ds.fb_c0 = ds.pad = 0;
+    ds.kind = 0; ds.cnt = ds.ncur = ds.c0 = ds.chan_bytes = ds.pitch_bytes = ds.pad0 = ds.pad1 = 0;
     if (unit >= c.n_units) {
       const int f = unit - c.n_units;
-      ds.kind = 1; ds.fb_roi = w.fb_list[f / fb_chunks]; ds.fb_c0 = (f % fb_chunks) * 32;
+      ds.kind = 1; ds.cnt = w.fb_list[f / fb_chunks]; ds.c0 = (f % fb_chunks) * 32;
       publish(ds, nullptr, 0);
       continue;
     }
@@ -754,9 +750,9 @@ __device__ __forceinline__ void s4_producer(const FpnDesc& d, const PlanCfg& c, 
         bulk_g2s(smem + 2 * buf_bytes + (size_t)tb * kS4TabBytes, w.tabg + (size_t)(lst + rc) * kS4RoiEnt,
                  (uint32_t)(nr * kS4RoiEnt * 8), &ctl->tfull[tb]);
       }
-      ds.tb = tb; ds.cnt = nr;
+      ds.cnt = nr;
       for (int i = i0; i < i1; ++i) {
-        ds.first = i == i0; ds.last = i == i1 - 1;
+        ds.kind = 0 | ((i == i0) << 8) | ((i == i1 - 1) << 9) | (tb << 10);
         ds.c0 = i * v.cg;
         ds.ncur = min(v.cg, c.C - ds.c0);
         publish(ds, d.feat[l] + (((size_t)img * c.C + ds.c0) * v.H + r0) * v.W, plane_sz);
@@ -765,8 +761,7 @@ __device__ __forceinline__ void s4_producer(const FpnDesc& d, const PlanCfg& c, 
     }
   }
   S4Desc ds;
-  ds.kind = 2; ds.first = ds.last = ds.tb = ds.cnt = ds.ncur = ds.c0 = ds.chan_bytes = ds.pitch_bytes = 0;
-  ds.fb_roi = ds.fb_c0 = ds.pad = 0;
+  ds.kind = 2; ds.cnt = ds.ncur = ds.c0 = ds.chan_bytes = ds.pitch_bytes = ds.pad0 = ds.pad1 = 0;
   publish(ds, nullptr, 0);
 }
 
@@ -807,14 +802,16 @@ roi_align_stream_fwd_kernel(const __grid_constant__ FpnDesc d, const __grid_cons
   const bool st0 = lane_on && t4 < PH, st1 = lane_on && t4 + 4 < PH;
   const int tap_off = odd ? 4 : 0;
   uint32_t m = 0, u = 0;
+  int rot = 0;                   // job rotation: += 11 (mod consumer warps) per message
   for (;;) {
     const int b = m & 1;
     mbar_wait(&ctl->full[b], (m >> 1) & 1u);
-    const S4Desc* dp = &ctl->desc[b];
-    const int kind = dp->kind;
+    const int4 d0 = reinterpret_cast<const int4*>(&ctl->desc[b])[0];
+    const int4 d1 = reinterpret_cast<const int4*>(&ctl->desc[b])[1];
+    const int kind = d0.x & 0xff;
     if (kind == 2) break;
     if (kind == 1) {
-      const int fb_roi = dp->fb_roi, fb_c0 = dp->fb_c0;
+      const int fb_roi = d0.y, fb_c0 = d0.w;
       const RoiGeom g = roi_geom(d, rois, levels, fb_roi, c.PH, c.PW, c.sr, c.finest);
       gather_roi_chunk<false>(d, g, fb_roi, fb_c0, min(32, c.C - fb_c0), out, c.PH, c.PW, tid, Tc);
       __syncwarp();
@@ -822,16 +819,18 @@ roi_align_stream_fwd_kernel(const __grid_constant__ FpnDesc d, const __grid_cons
       ++m;
       continue;
     }
-    const int tb = dp->tb, cnt = dp->cnt, ncur = dp->ncur, c0 = dp->c0;
-    const int chan_bytes = dp->chan_bytes, pitch_bytes = dp->pitch_bytes;
-    const bool first = dp->first, last = dp->last;
+    const int tb = (d0.x >> 10) & 1, cnt = d0.y, ncur = d0.z, c0 = d0.w;
+    const int chan_bytes = d1.x, pitch_bytes = d1.y;
+    const bool first = (d0.x >> 8) & 1, last = (d0.x >> 9) & 1;
     if (first) mbar_wait(&ctl->tfull[tb], (u >> 1) & 1u);
     const unsigned char* tabs = smem + 2 * buf_bytes + (size_t)tb * kS4TabBytes;
     const char* bufb = reinterpret_cast<const char*>(smem + b * buf_bytes) + tap_off;
     // jobs of a buffer are equal-sized: static round-robin, rotated per message so that the warps that get
     // the extra job of a partial round change from buffer to buffer (no counter, no atomics)
-    int k0 = cw + (int)((m * 11u) % (uint32_t)n_cwarps);
+    int k0 = cw + rot;
     if (k0 >= n_cwarps) k0 -= n_cwarps;
+    rot += 11;
+    if (rot >= n_cwarps) rot -= n_cwarps;
     for (int k = k0; k < cnt; k += n_cwarps) {
       const uint2* te = reinterpret_cast<const uint2*>(tabs + (size_t)k * (kS4RoiEnt * 8));
       const uint4* y4 = reinterpret_cast<const uint4*>(te);

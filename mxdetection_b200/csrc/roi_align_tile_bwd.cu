@@ -216,10 +216,15 @@ __global__ void __launch_bounds__(256) tplan_rois_kernel(FpnDesc d, TCfg c, TWs 
   }
 }
 
-// Exclusive scan of the tile counts and the per-tile RoI lists (single CTA).
+// Exclusive scan of the tile counts and the per-tile RoI lists (single CTA).  The list cursors live in shared
+// memory when the tile table fits (global atomics put two L2 round trips on every RoI of the fill loop).
+constexpr int kTbSmemTiles = 4096;
+
 __global__ void __launch_bounds__(1024) tplan_group_kernel(TCfg c, TWs w, int R) {
   __shared__ int s_part[1024];
+  __shared__ int s_pos[kTbSmemTiles];      // next free slot of every tile's list
   const int tid = threadIdx.x;
+  const bool in_smem = c.NT <= kTbSmemTiles;
   const int per = (c.NT + 1023) / 1024;
   int sum = 0;
   for (int i = tid * per; i < min(c.NT, (tid + 1) * per); ++i) sum += w.cnt[i];
@@ -234,6 +239,7 @@ __global__ void __launch_bounds__(1024) tplan_group_kernel(TCfg c, TWs w, int R)
   int run = s_part[tid] - sum;
   for (int i = tid * per; i < min(c.NT, (tid + 1) * per); ++i) {
     w.start[i] = run;
+    if (in_smem) s_pos[i] = run;
     run += w.cnt[i];
   }
   __syncthreads();
@@ -247,7 +253,8 @@ __global__ void __launch_bounds__(1024) tplan_group_kernel(TCfg c, TWs w, int R)
     for (int ty = tya; ty <= tyb; ++ty)
       for (int tx = txa; tx <= txb; ++tx) {
         const int t = h1.x * c.tiles_per_img + v.tile_base + ty * v.ntx + tx;
-        w.pairs[w.start[t] + atomicAdd(&w.cursor[t], 1)] = n;
+        const int pos = in_smem ? atomicAdd(&s_pos[t], 1) : w.start[t] + atomicAdd(&w.cursor[t], 1);
+        w.pairs[pos] = n;
       }
   }
 }
