@@ -54,6 +54,34 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+CURRENT_NCU_SUMMARY = "ncu_r1h.txt"     # `ncu --set full` capture of the kernels this tree ships (profiles/README.md)
+
+
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
+    `ncu --set full` summary under profiles/ (profiles/summarize.py writes them); None when there is none."""
+    import glob
+    import re
+    best = None
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_*.txt")))
+    cur = os.path.join(ROOT, "profiles", CURRENT_NCU_SUMMARY)
+    for path in [q for q in paths if q != cur] + ([cur] if os.path.exists(cur) else []):   # the current build's capture wins
+        txt = open(path).read()
+        for blk in txt.split("== ncu --set full:")[1:]:
+            if kernel_substr not in blk.splitlines()[0]:
+                continue
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                m = re.search(key + r"\s+([0-9.]+)\s+(\w+)", blk)
+                if not m:
+                    tot = None
+                    break
+                tot += float(m.group(1)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(2), 1.0)
+            if tot:
+                best = (tot, os.path.relpath(path, ROOT))
+    return best
+
+
 class ClockSampler:
     """SM clock / throttle-reason sampling DURING the timed region (NVML polled from a thread every ~2 ms;
     same fields as the nvidia-smi recipe of B200_PROFILING.md, which is too slow to start for a 50 ms region)."""
@@ -268,9 +296,11 @@ def run_ours(args):
     alg_bwd = out_bytes + map_bytes                   # read grad_out + write every grad-map byte (req=write)
     dom = "roi_align_backward" if bwd_ms >= fwd_ms else "roi_align_forward"
     dom_ms = max(fwd_ms, bwd_ms); dom_bytes = alg_bwd if bwd_ms >= fwd_ms else alg_fwd
+    traffic = ncu_traffic("roi_align_tile_bwd_kernel" if bwd_ms >= fwd_ms else "roi_align_stream_fwd_kernel")
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak_gbs, "traffic": (traffic[0] if traffic else None),
+                "traffic_source": (traffic[1] if traffic else None), "peak_source": peak_src,
                 "algorithmic_bytes": dom_bytes, "avg_ms": dom_ms,
                 "forward": {"ms": fwd_ms, "bytes": alg_fwd, "gbs": alg_fwd / fwd_ms / 1e6, "frac": alg_fwd / fwd_ms / 1e6 / peak_gbs,
                             "map_bytes": map_bytes, "touched_bytes": tb},

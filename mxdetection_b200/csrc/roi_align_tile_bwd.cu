@@ -459,7 +459,7 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
     for (int i = lane; i < kTbRowWords; i += 32) trow[i] = 0.0f;
   __syncwarp();
   int m = 0;
-  bool have = false;
+  bool have = false, touched = false;    // touched: some RoI of the item reached this warp's row
   int lvl = 0, img = 0, c0 = 0, ty0 = 0, tx0 = 0, th = 0, tw = 0, H = 0, W = 0;
   auto write_row = [&](bool zeros) {
     const int gy = ty0 + warp;
@@ -502,14 +502,16 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
     const int hd = reinterpret_cast<const int*>(st)[0];
     const int kind = hd & 0xff;
     if (kind == kMsgPair) {
-      if (warp >= ((hd >> 8) & 0xff) && warp <= (hd >> 16))
+      if (warp >= ((hd >> 8) & 0xff) && warp <= (hd >> 16)) {
+        touched = true;
         tb_row<PW>(reinterpret_cast<const float*>(st + c.off_g) + lane * c.bins,
                    reinterpret_cast<const uint2*>(st + c.off_rt) + warp * 4,
                    reinterpret_cast<const uint4*>(st + c.off_xt), reinterpret_cast<char*>(trow + lane),
                    2.0f * c.inv_count);
+      }
     } else {
-      if (have) write_row(false);
-      have = false;
+      if (have) write_row(!touched);     // an untouched row is still all zero: store zeros, skip the LDS / STS pass
+      have = false; touched = false;
       if (kind == kMsgStop) break;
       const int4 h1 = reinterpret_cast<const int4*>(st)[1];
       lvl = h1.x; img = h1.y; c0 = h1.z; ty0 = h1.w & 0xffff; tx0 = h1.w >> 16;
