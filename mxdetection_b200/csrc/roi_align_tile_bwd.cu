@@ -159,29 +159,38 @@ __global__ void __launch_bounds__(256) tplan_rois_kernel(FpnDesc d, TCfg c, TWs 
   ok = ok && Hf >= 1 && Hf <= c.max_hf && y0 >= 0 && x0 >= 0;
   bool rows_ok = true;
   if (ok) {
+    // dense rows: bin weights accumulate in 7 registers (static index: PH = 7, sr = 2 here), then shift to the
+    // first non-zero bin - no local-memory array
     for (int i0 = 0; i0 < Hf; i0 += 32) {
       const int i = i0 + lane;
       const int row = y0 + i;
-      int pa = -1, pl = -1;
-      float wr[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int t = 0; t < c.ty; ++t) {
+      float wabs[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < 14; ++t) {
         const int lo_t = __shfl_sync(full, ylo, t);
         const float l_t = __shfl_sync(full, yl, t);
         float wt = 0.0f;
         if (lo_t == row) wt = 1.0f - l_t;
         else if (lo_t + 1 == row) wt = l_t;
-        if (wt != 0.0f) {
-          const int ph = t / c.sr;
-          if (pa < 0) pa = ph;
-          const int k = ph - pa;
-          if (k < 7) wr[k] += wt; else rows_ok = false;
-          pl = ph;
-        }
+        wabs[t >> 1] += wt;
       }
+      int pa = -1, pl = -1;
+#pragma unroll
+      for (int k = 0; k < 7; ++k)
+        if (wabs[k] != 0.0f) { if (pa < 0) pa = k; pl = k; }
       if (i < Hf) {
         const int nph = pa < 0 ? 0 : pl - pa + 1;
+        const int p0 = pa < 0 ? 0 : pa;
+        float wr[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          float v = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 7; ++j) if (j == p0 + k) v = wabs[j];
+          wr[k] = v;
+        }
         uint4* rec = w.rowtab + ((size_t)n * c.max_hf + i) * 2;
-        rec[0] = make_uint4((unsigned)(pa < 0 ? 0 : pa) | ((unsigned)nph << 8), __float_as_uint(wr[0]),
+        rec[0] = make_uint4((unsigned)p0 | ((unsigned)nph << 8), __float_as_uint(wr[0]),
                             __float_as_uint(wr[1]), __float_as_uint(wr[2]));
         rec[1] = make_uint4(__float_as_uint(wr[3]), __float_as_uint(wr[4]), __float_as_uint(wr[5]),
                             __float_as_uint(wr[6]));
