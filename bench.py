@@ -320,7 +320,7 @@ def run_ours(args):
     d2h = out_h.numel() * 4 + sum(t.numel() * 4 for t in grads_h)
 
     from mxdetection_b200.ops import HostRoIStage
-    stage = HostRoIStage(shapes, ROIS_PER_IMG, POOLED, scales, 2, dev, depth=2)
+    stage = HostRoIStage(shapes, ROIS_PER_IMG, POOLED, scales, 2, dev, depth=2)   # whole images: profiles/e2e_sweep.py
 
     def e2e_step():
         # public host-buffer API: per-image pipeline H2D | fwd+bwd | D2H (every byte still crosses PCIe inside the step)

@@ -48,6 +48,10 @@ extern "C" {
 int mxd_version(void);                /* 10000*major + 100*minor + patch        */
 const char* mxd_last_error(void);     /* thread-local, valid until next call    */
 uint64_t mxd_launch_count(void);      /* kernels enqueued by this library so far */
+/* Host plumbing of the host-buffer RoI stage (ops.HostRoIStage): strided copy of `rows` runs of
+ * `width_bytes` between pinned host memory and the device (kind 1 = H2D, 2 = D2H), async on stream. */
+int mxd_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                     size_t width_bytes, size_t rows, int kind, void* stream);
 
 /* ---- A1/A2  RoIAlign  (mxdetection/ops, /root/reference/README.md:24;
  *      contract mx.nd.contrib.ROIAlign + _backward_ROIAlign, mxnet 1.3.0

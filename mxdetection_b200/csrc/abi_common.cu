@@ -46,4 +46,17 @@ int mxd_version(void) { return 100; /* 0.1.0 */ }
 const char* mxd_last_error(void) { return mxd::g_err; }
 int mxd_sizeof_rpn_config(void) { return (int)sizeof(mxd_rpn_config); }
 uint64_t mxd_launch_count(void) { return mxd::g_launches.load(std::memory_order_relaxed); }
+
+// Strided host<->device copy of `rows` runs of `width_bytes` (cudaMemcpy2DAsync): the host-buffer RoI stage moves
+// channel slices of (R, C, PH, PW) tensors without first compacting them on the CPU.  kind: 1 = H2D, 2 = D2H.
+int mxd_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                     int kind, void* stream) {
+  using namespace mxd;
+  MXD_REQUIRE(kind == 1 || kind == 2, MXD_EINVAL, "kind must be 1 (H2D) or 2 (D2H)");
+  if (width_bytes == 0 || rows == 0) return MXD_OK;
+  MXD_REQUIRE(dst && src && dst_pitch >= width_bytes && src_pitch >= width_bytes, MXD_EINVAL, "bad 2-D copy geometry");
+  MXD_CUDA_OK(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows,
+                                kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, as_stream(stream)));
+  return MXD_OK;
+}
 }

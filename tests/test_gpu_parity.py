@@ -217,14 +217,16 @@ def test_host_roi_stage_pipeline_matches_device_path():
     rois_h = torch.from_numpy(d["rois"]).pin_memory(); gout_h = torch.from_numpy(d["grad_out"]).pin_memory()
     out_h = torch.empty(d["grad_out"].shape).pin_memory()
     grads_h = [torch.empty(f.shape).pin_memory() for f in d["feats"]]
-    stage = HostRoIStage([f.shape for f in d["feats"]], 64, (7, 7), d["scales"], 2, DEV, depth=2)
-    for _ in range(2):                                               # second call re-uses the slots
-        stage.forward_backward(feats_h, rois_h, gout_h, out_h, grads_h).synchronize()
     ref = roi_align_fpn_forward([T(f) for f in d["feats"]], T(d["rois"]), (7, 7), d["scales"], 2)
     gref = roi_align_fpn_backward(T(d["grad_out"]), T(d["rois"]), [f.shape for f in d["feats"]], (7, 7), d["scales"], 2)
-    assert close(out_h.numpy(), N(ref), 1e-6)
-    for a, b in zip(grads_h, gref):
-        assert close(a.numpy(), N(b), 1e-4)
+    for split in (1, 2):                                             # whole images / two channel slices per image
+        stage = HostRoIStage([f.shape for f in d["feats"]], 64, (7, 7), d["scales"], 2, DEV, depth=2, channel_split=split)
+        for _ in range(2):                                           # second call re-uses the slots
+            out_h.zero_(); [g.zero_() for g in grads_h]
+            stage.forward_backward(feats_h, rois_h, gout_h, out_h, grads_h).synchronize()
+        assert close(out_h.numpy(), N(ref), 1e-6)
+        for a, b in zip(grads_h, gref):
+            assert close(a.numpy(), N(b), 1e-4)
 
 
 def test_mask_branch_cfg4_14x14():
