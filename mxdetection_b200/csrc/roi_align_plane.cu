@@ -29,8 +29,8 @@ constexpr int kSmallRing = 8 * 1024;
 constexpr int kMiscBytes = 512;              // mbarrier + scalars + staged RoI ids
 // stream forward kernel (7x7 / sample_ratio 2): two band buffers + two table buffers per CTA
 constexpr int kS4TabBytes = 16 * 1024;       // one table buffer
-constexpr int kS4RoiEnt = 30;                // 28 tap entries + {RoI id, 0} + pad = 240 bytes (16-byte multiple)
-constexpr int kS4MaxRois = kS4TabBytes / (kS4RoiEnt * 8);
+// grouped table of one RoI: ty + tx tap entries + {RoI id, 0}, padded to an even count (16-byte multiple)
+static inline int s4_ent(int entries) { return (entries + 2) & ~1; }
 constexpr int kS4KC = 4;                     // items (channel groups) per work unit
 constexpr int kS4CtlBytes = 512;
 
@@ -53,7 +53,7 @@ struct PlanCfg {
   int bands_per_img, NB, n_plane_items;
   int budget_floats, chunk_rois, tab_bytes, slot_bytes;
   int threads, smem_bytes, ctas_per_sm, group;
-  int stream, n_units;
+  int stream, n_units, s4_ent, s4_max_rois;
   float finest;
 };
 
@@ -67,7 +67,7 @@ struct PlanWs {
   int* list;     // [R] RoI ids grouped by band
   int* fb_list;  // [R] RoIs for the gather fallback
   uint2* tab;    // [R][ty+tx] packed {offset | hi_bit<<31, lo-weight bits}
-  uint2* tabg;   // [R][kS4RoiEnt] the same tables in band-grouped order + {RoI id, 0} (stream kernel)
+  uint2* tabg;   // [R][s4_ent] the same tables in band-grouped order + {RoI id, 0} (stream kernel)
   size_t bytes;
 };
 
@@ -84,7 +84,7 @@ static PlanWs carve_plan(void* base, int R, int NB, int entries) {
   w.list = (int*)take(sizeof(int) * (size_t)(R > 0 ? R : 1));
   w.fb_list = (int*)take(sizeof(int) * (size_t)(R > 0 ? R : 1));
   w.tab = (uint2*)take(sizeof(uint2) * (size_t)(R > 0 ? R : 1) * entries);
-  w.tabg = (uint2*)take(sizeof(uint2) * (size_t)(R > 0 ? R : 1) * kS4RoiEnt);
+  w.tabg = (uint2*)take(sizeof(uint2) * (size_t)(R > 0 ? R : 1) * s4_ent(entries));
   w.bytes = off;
   return w;
 }
@@ -93,9 +93,11 @@ static PlanWs carve_plan(void* base, int R, int NB, int entries) {
 static bool make_cfg(int N, int C, int L, const int* Hs, const int* Ws, int PH, int PW, int sr, float finest,
                      PlanCfg* c, bool stream = false) {
   if (sr <= 0 || PH * sr > 64 || PW * sr > 32) return false;   // adaptive / very fine sampling: gather kernels
-  if (stream && (sr != 2 || PH != 7 || PW != 7)) return false;
+  if (stream && (sr != 2 || !((PH == 7 && PW == 7) || (PH == 14 && PW == 14)))) return false;
   memset(c, 0, sizeof(*c));
   c->stream = stream ? 1 : 0;
+  c->s4_ent = s4_ent(PH * sr + PW * sr);
+  c->s4_max_rois = kS4TabBytes / (c->s4_ent * 8);
   c->L = L; c->N = N; c->C = C; c->PH = PH; c->PW = PW; c->sr = sr; c->ty = PH * sr; c->tx = PW * sr;
   c->finest = finest;
   const int entry_bytes = (c->ty + c->tx) * (int)sizeof(uint2);
@@ -124,7 +126,7 @@ static bool make_cfg(int N, int C, int L, const int* Hs, const int* Ws, int PH, 
   c->budget_floats = ((smem_cta - c->tab_bytes - kMiscBytes) / 4) & ~3;
   if (stream) {
     if (big) return false;                 // a plane that only fits whole: the one-CTA plane kernel keeps it resident
-    c->ctas_per_sm = 1; c->threads = 1024; c->tab_bytes = 2 * kS4TabBytes;
+    c->ctas_per_sm = 1; c->threads = (4 * PW <= 32) ? 1024 : 768; c->tab_bytes = 2 * kS4TabBytes;
     c->budget_floats = (((kSmemLimit - 2 * kS4TabBytes - kS4CtlBytes) / 2) / 4) & ~3;
   }
   if (c->budget_floats < 4096) return false;
@@ -285,14 +287,14 @@ __global__ void __launch_bounds__(1024) plan_group_kernel(PlanCfg c, PlanWs w, i
 // Stream kernel: the tables in band-grouped order, so one bulk copy brings a band's RoIs to shared memory.
 __global__ void __launch_bounds__(256) plan_pack_kernel(PlanCfg c, PlanWs w, int R) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int pos = i / kS4RoiEnt, e = i - pos * kS4RoiEnt;
+  const int pos = i / c.s4_ent, e = i - pos * c.s4_ent;
   const int ent = c.ty + c.tx;
   if (pos >= R - w.hdr[1]) return;                // planned RoIs = all but the fallback ones
   const int n = w.list[pos];
   uint2 v = make_uint2(0u, 0u);
   if (e < ent) v = w.tab[(size_t)n * ent + e];
   else if (e == ent) v = make_uint2((unsigned)n, 0u);
-  w.tabg[(size_t)pos * kS4RoiEnt + e] = v;
+  w.tabg[(size_t)pos * c.s4_ent + e] = v;
 }
 
 __device__ __forceinline__ float ldf(const char* p) { return *reinterpret_cast<const float*>(p); }
@@ -741,14 +743,14 @@ __device__ __forceinline__ void s4_producer(const FpnDesc& d, const PlanCfg& c, 
     const int i0 = chunk * v.kc, i1 = min(v.ncg, i0 + v.kc);
     ds.chan_bytes = nrows * v.W * 4;
     ds.pitch_bytes = v.W * 4;
-    for (int rc = 0; rc < cnt; rc += kS4MaxRois) {
-      const int nr = min(kS4MaxRois, cnt - rc);
+    for (int rc = 0; rc < cnt; rc += c.s4_max_rois) {
+      const int nr = min(c.s4_max_rois, cnt - rc);
       const int tb = u & 1;
       mbar_wait(&ctl->tempty[tb], ((u >> 1) & 1u) ^ 1u);
       if (lane == 0) {
-        mbar_arrive_expect_tx(&ctl->tfull[tb], (uint32_t)(nr * kS4RoiEnt * 8));
-        bulk_g2s(smem + 2 * buf_bytes + (size_t)tb * kS4TabBytes, w.tabg + (size_t)(lst + rc) * kS4RoiEnt,
-                 (uint32_t)(nr * kS4RoiEnt * 8), &ctl->tfull[tb]);
+        mbar_arrive_expect_tx(&ctl->tfull[tb], (uint32_t)(nr * c.s4_ent * 8));
+        bulk_g2s(smem + 2 * buf_bytes + (size_t)tb * kS4TabBytes, w.tabg + (size_t)(lst + rc) * c.s4_ent,
+                 (uint32_t)(nr * c.s4_ent * 8), &ctl->tfull[tb]);
       }
       ds.cnt = nr;
       for (int i = i0; i < i1; ++i) {
@@ -766,13 +768,15 @@ __device__ __forceinline__ void s4_producer(const FpnDesc& d, const PlanCfg& c, 
 }
 
 template <int PH, int PW>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__((4 * PW <= 32) ? 1024 : 768, 1)     // 14x14 carries 14 accumulators: 85 registers
 roi_align_stream_fwd_kernel(const __grid_constant__ FpnDesc d, const __grid_constant__ PlanCfg c, PlanWs w,
                             const float* __restrict__ rois, const int* __restrict__ levels,
                             float* __restrict__ out) {
-  static_assert(4 * PW <= 32 && PH <= 8, "lane = x tap, 8 accumulators");
+  // lane = x TAP when the 4*PW taps fit a warp (7x7), else lane = x SAMPLE with both taps loaded by the lane (14x14)
+  constexpr bool TAPLANE = 4 * PW <= 32;
+  static_assert(TAPLANE ? PH <= 8 : (2 * PW <= 32 && PH % 2 == 0 && PH <= 16), "lane mapping");
   constexpr int TY = 2 * PH, TX = 2 * PW, BINS = PH * PW;
-  static_assert(TY + TX + 1 <= kS4RoiEnt, "table entry layout");
+  constexpr int ENT = (TY + TX + 2) & ~1;
   extern __shared__ __align__(128) unsigned char smem[];
   const size_t buf_bytes = (size_t)c.budget_floats * 4;
   S4Ctl* ctl = reinterpret_cast<S4Ctl*>(smem + 2 * buf_bytes + 2 * kS4TabBytes);
@@ -794,13 +798,13 @@ roi_align_stream_fwd_kernel(const __grid_constant__ FpnDesc d, const __grid_cons
     return;
   }
   const int lane = tid & 31, cw = tid >> 5;
-  const int xs = min(lane >> 1, TX - 1);
-  const bool lane_on = lane < 2 * TX;
-  const int t4 = lane & 3, pw = min(lane >> 2, PW - 1);
+  const int xs = TAPLANE ? min(lane >> 1, TX - 1) : min(lane, TX - 1);
+  const bool lane_on = TAPLANE ? lane < 2 * TX : lane < TX;
+  const int t4 = lane & 3, pw = TAPLANE ? min(lane >> 2, PW - 1) : min(lane >> 1, PW - 1);
   const bool odd = lane & 1, up = lane & 2;
   const int o0 = t4 * PW + pw, o1 = (t4 + 4) * PW + pw;
   const bool st0 = lane_on && t4 < PH, st1 = lane_on && t4 + 4 < PH;
-  const int tap_off = odd ? 4 : 0;
+  const int tap_off = (TAPLANE && odd) ? 4 : 0;
   uint32_t m = 0, u = 0;
   int rot = 0;                   // job rotation: += 11 (mod consumer warps) per message
   for (;;) {
@@ -832,46 +836,79 @@ roi_align_stream_fwd_kernel(const __grid_constant__ FpnDesc d, const __grid_cons
     rot += 11;
     if (rot >= n_cwarps) rot -= n_cwarps;
     for (int k = k0; k < cnt; k += n_cwarps) {
-      const uint2* te = reinterpret_cast<const uint2*>(tabs + (size_t)k * (kS4RoiEnt * 8));
+      const uint2* te = reinterpret_cast<const uint2*>(tabs + (size_t)k * (ENT * 8));
       const uint4* y4 = reinterpret_cast<const uint4*>(te);
       const int n = (int)te[TY + TX].x;
       const uint2 xc = te[TY + xs];
       const float lx = __uint_as_float(xc.y);
-      const float wx = lane_on ? (odd ? lx : 1.0f - lx) * 0.25f : 0.0f;
       const char* px = bufb + xc.x;
       float* o = out + ((size_t)n * c.C + c0) * BINS;
-      for (int j = 0; j < ncur; ++j) {
-        float acc[8];
+      if constexpr (TAPLANE) {
+        const float wx = lane_on ? (odd ? lx : 1.0f - lx) * 0.25f : 0.0f;
+        for (int j = 0; j < ncur; ++j) {
+          float acc[8];
 #pragma unroll
-        for (int ph = 0; ph < PH; ++ph) {
-          const uint4 e = y4[ph];         // samples 2ph, 2ph+1: {row offset, l} each
-          const char* r0 = px + e.x;
-          const char* r1 = px + e.z;
-          const float v00 = ldf(r0), v01 = ldf(r0 + pitch_bytes), v10 = ldf(r1), v11 = ldf(r1 + pitch_bytes);
-          const float a = fmaf(__uint_as_float(e.y), v01 - v00, v00);
-          const float bq = fmaf(__uint_as_float(e.w), v11 - v10, v10);
-          acc[ph] = (a + bq) * wx;
+          for (int ph = 0; ph < PH; ++ph) {
+            const uint4 e = y4[ph];         // samples 2ph, 2ph+1: {row offset, l} each
+            const char* r0 = px + e.x;
+            const char* r1 = px + e.z;
+            const float v00 = ldf(r0), v01 = ldf(r0 + pitch_bytes), v10 = ldf(r1), v11 = ldf(r1 + pitch_bytes);
+            const float a = fmaf(__uint_as_float(e.y), v01 - v00, v00);
+            const float bq = fmaf(__uint_as_float(e.w), v11 - v10, v10);
+            acc[ph] = (a + bq) * wx;
+          }
+#pragma unroll
+          for (int ph = PH; ph < 8; ++ph) acc[ph] = 0.0f;
+          float r[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float keep = odd ? acc[2 * q + 1] : acc[2 * q];
+            const float send = odd ? acc[2 * q] : acc[2 * q + 1];
+            r[q] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+          float s2[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float keep = up ? r[2 * q + 1] : r[2 * q];
+            const float send = up ? r[2 * q] : r[2 * q + 1];
+            s2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+          if (st0) o[o0] = s2[0];
+          if (st1) o[o1] = s2[1];
+          px += chan_bytes;
+          o += BINS;
         }
+      } else {
+        // lane = x sample: the lane loads both taps of its sample ([r], [r+4]: one address, one immediate) on
+        // both rows, interpolates in x then y; the two lanes of a bin swap half of their PH sums
+        const float* ob = o + pw;
+        for (int j = 0; j < ncur; ++j) {
+          float acc[PH];
 #pragma unroll
-        for (int ph = PH; ph < 8; ++ph) acc[ph] = 0.0f;
-        float r[4];
+          for (int ph = 0; ph < PH; ++ph) {
+            // volatile load: re-read the row entries per channel instead of parking 56 registers across the loop
+            uint4 e;
+            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
+                         : "r"(smem_u32(y4 + ph)));
+            const char* r0 = px + e.x;
+            const char* r1 = px + e.z;
+            const float a00 = ldf(r0), a01 = ldf(r0 + 4), a10 = ldf(r0 + pitch_bytes), a11 = ldf(r0 + pitch_bytes + 4);
+            const float b00 = ldf(r1), b01 = ldf(r1 + 4), b10 = ldf(r1 + pitch_bytes), b11 = ldf(r1 + pitch_bytes + 4);
+            const float at = fmaf(lx, a01 - a00, a00), ab = fmaf(lx, a11 - a10, a10);
+            const float bt = fmaf(lx, b01 - b00, b00), bb = fmaf(lx, b11 - b10, b10);
+            acc[ph] = fmaf(__uint_as_float(e.y), ab - at, at) + fmaf(__uint_as_float(e.w), bb - bt, bt);
+          }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float keep = odd ? acc[2 * q + 1] : acc[2 * q];
-          const float send = odd ? acc[2 * q] : acc[2 * q + 1];
-          r[q] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          for (int q = 0; q < PH / 2; ++q) {
+            const float keep = odd ? acc[2 * q + 1] : acc[2 * q];
+            const float send = odd ? acc[2 * q] : acc[2 * q + 1];
+            const float v = (keep + __shfl_xor_sync(0xffffffffu, send, 1)) * 0.25f;
+            if (lane_on) const_cast<float*>(ob)[(2 * q + (odd ? 1 : 0)) * PW] = v;
+          }
+          px += chan_bytes;
+          ob += BINS;
         }
-        float s2[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const float keep = up ? r[2 * q + 1] : r[2 * q];
-          const float send = up ? r[2 * q] : r[2 * q + 1];
-          s2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-        if (st0) o[o0] = s2[0];
-        if (st1) o[o1] = s2[1];
-        px += chan_bytes;
-        o += BINS;
       }
     }
     __syncwarp();
@@ -1113,15 +1150,20 @@ int plane_forward(const FpnDesc& d, const float* rois, const int* levels, float*
   int rc;
   if ((rc = run_planner(d, c, w, rois, levels, R, 0, st))) return rc;
   if (stream) {
-    plan_pack_kernel<<<(R * kS4RoiEnt + 255) / 256, 256, 0, st>>>(c, w, R);
+    plan_pack_kernel<<<(R * c.s4_ent + 255) / 256, 256, 0, st>>>(c, w, R);
     MXD_POST_LAUNCH("roi_align_plan_pack");
     static bool attr4 = false;
     if (!attr4) {
       MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_stream_fwd_kernel<7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemLimit));
+      MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_stream_fwd_kernel<14, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kSmemLimit));
       attr4 = true;
     }
-    roi_align_stream_fwd_kernel<7, 7><<<num_sms(), c.threads, c.smem_bytes, st>>>(d, c, w, rois, levels, out);
+    if (PH == 7)
+      roi_align_stream_fwd_kernel<7, 7><<<num_sms(), c.threads, c.smem_bytes, st>>>(d, c, w, rois, levels, out);
+    else
+      roi_align_stream_fwd_kernel<14, 14><<<num_sms(), c.threads, c.smem_bytes, st>>>(d, c, w, rois, levels, out);
     MXD_POST_LAUNCH("roi_align_stream_fwd");
     *handled = 1;
     return MXD_OK;
