@@ -30,7 +30,7 @@ namespace mxd {
 
 constexpr int kTbWarps = 31;                       // consumer warps; warp w owns tile row w
 constexpr int kTbThreads = (kTbWarps + 1) * 32;    // + one producer warp
-constexpr int kTbStages = 9;
+constexpr int kTbMaxStages = 16;                   // ring depth is per configuration (9 for 7x7, 4 for 14x14)
 constexpr int kTbMaxHfCap = 256;                   // rows of the dense per-RoI row table: min(cap, tallest map)
 constexpr int kTbPix = 33;                         // words per tile pixel (32 channels + 1 pad)
 constexpr int kTbMaxTiles = 64;                    // tiles one RoI may intersect
@@ -48,7 +48,7 @@ struct TCfg {
   TLevel lv[MXD_MAX_LEVELS];
   int L, N, C, PH, PW, sr, ty, tx, bins;
   int tiles_per_img, NT, ncg, n_items;
-  int stage_bytes, off_xt, off_rt, off_g, tile_bytes, smem_bytes, max_rows, max_hf;
+  int stage_bytes, off_xt, off_rt, off_g, tile_bytes, smem_bytes, max_rows, max_hf, n_stages;
   int accumulate;
   float finest, inv_count;
 };
@@ -88,7 +88,7 @@ static TWs carve_tile(void* base, int R, int NT, int tx, int max_hf) {
 // instantiations exist; everything else keeps the RED kernels.
 static bool make_tcfg(int N, int C, int L, const int* Hs, const int* Ws, int PH, int PW, int sr, float finest,
                       int accumulate, TCfg* c) {
-  if (sr != 2 || PH != 7 || PW != 7 || (C & 31) != 0 || C == 0) return false;
+  if (sr != 2 || !((PH == 7 && PW == 7) || (PH == 14 && PW == 14)) || (C & 31) != 0 || C == 0) return false;
   memset(c, 0, sizeof(*c));
   c->L = L; c->N = N; c->C = C; c->PH = PH; c->PW = PW; c->sr = sr; c->ty = PH * sr; c->tx = PW * sr;
   c->bins = PH * PW; c->finest = finest; c->inv_count = 1.0f / (float)(sr * sr); c->accumulate = accumulate;
@@ -96,7 +96,8 @@ static bool make_tcfg(int N, int C, int L, const int* Hs, const int* Ws, int PH,
   c->off_rt = (int)align_up((size_t)c->off_xt + PW * 16, 32);
   c->off_g = c->off_rt + kTbMaxTh * 32;
   c->stage_bytes = (int)align_up((size_t)c->off_g + 32 * c->bins * 4, 128);
-  c->tile_bytes = (kTbSmem - kTbStages * c->stage_bytes - 256) & ~15;
+  c->n_stages = PW == 7 ? 9 : 4;                    // 7.5 KB / 26 KB of grad_out per stage
+  c->tile_bytes = (kTbSmem - c->n_stages * c->stage_bytes - 256) & ~15;
   const int max_rows = c->tile_bytes / (kTbRowWords * 4);
   c->max_rows = max_rows;
   int base = 0;
@@ -119,12 +120,13 @@ static bool make_tcfg(int N, int C, int L, const int* Hs, const int* Ws, int PH,
   c->ncg = C / 32;
   if ((long long)c->NT * c->ncg > 0x3fffffffLL) return false;
   c->n_items = c->NT * c->ncg;
-  c->smem_bytes = c->tile_bytes + kTbStages * c->stage_bytes + 256;
+  c->smem_bytes = c->tile_bytes + c->n_stages * c->stage_bytes + 256;
   return c->NT > 0;
 }
 
 // ------------------------------------------------------------------- planner ------
 // One warp per RoI: Spec A sample tables -> dense row table, packed x taps, tile counts.
+template <int PH>
 __global__ void __launch_bounds__(256) tplan_rois_kernel(FpnDesc d, TCfg c, TWs w, const float* __restrict__ rois,
                                                           const int* __restrict__ levels, int R) {
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -159,14 +161,16 @@ __global__ void __launch_bounds__(256) tplan_rois_kernel(FpnDesc d, TCfg c, TWs 
   ok = ok && Hf >= 1 && Hf <= c.max_hf && y0 >= 0 && x0 >= 0;
   bool rows_ok = true;
   if (ok) {
-    // dense rows: bin weights accumulate in 7 registers (static index: PH = 7, sr = 2 here), then shift to the
-    // first non-zero bin - no local-memory array
+    // dense rows: bin weights accumulate in PH registers (static index: sr = 2 here), then shift to the first
+    // non-zero bin - no local-memory array.  A row fed by more than 7 bins (bin height < 0.3 px) goes to the fallback.
     for (int i0 = 0; i0 < Hf; i0 += 32) {
       const int i = i0 + lane;
       const int row = y0 + i;
-      float wabs[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float wabs[PH];
 #pragma unroll
-      for (int t = 0; t < 14; ++t) {
+      for (int k = 0; k < PH; ++k) wabs[k] = 0.0f;
+#pragma unroll
+      for (int t = 0; t < 2 * PH; ++t) {
         const int lo_t = __shfl_sync(full, ylo, t);
         const float l_t = __shfl_sync(full, yl, t);
         float wt = 0.0f;
@@ -176,17 +180,18 @@ __global__ void __launch_bounds__(256) tplan_rois_kernel(FpnDesc d, TCfg c, TWs 
       }
       int pa = -1, pl = -1;
 #pragma unroll
-      for (int k = 0; k < 7; ++k)
+      for (int k = 0; k < PH; ++k)
         if (wabs[k] != 0.0f) { if (pa < 0) pa = k; pl = k; }
       if (i < Hf) {
         const int nph = pa < 0 ? 0 : pl - pa + 1;
         const int p0 = pa < 0 ? 0 : pa;
+        if (nph > 7) rows_ok = false;
         float wr[7];
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
           float v = 0.0f;
 #pragma unroll
-          for (int j = 0; j < 7; ++j) if (j == p0 + k) v = wabs[j];
+          for (int j = 0; j < PH; ++j) if (j == p0 + k) v = wabs[j];
           wr[k] = v;
         }
         uint4* rec = w.rowtab + ((size_t)n * c.max_hf + i) * 2;
@@ -270,8 +275,8 @@ __global__ void __launch_bounds__(1024) tplan_group_kernel(TCfg c, TWs w, int R)
 
 // --------------------------------------------------------------- main kernel ------
 struct TbCtl {
-  u64 full[kTbStages];
-  u64 empty[kTbStages];
+  u64 full[kTbMaxStages];
+  u64 empty[kTbMaxStages];
 };
 
 // The 4 x taps of bin pw (2 samples x lo/hi) as up to 4 DISTINCT tile columns with merged weights
@@ -297,7 +302,10 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
                                             const float* __restrict__ gout, unsigned char* stages, TbCtl* ctl,
                                             int lane) {
   const unsigned full = 0xffffffffu;
-  int m = 0;
+  const int S = c.n_stages;
+  int s = 0;
+  uint32_t par = 1;     // parity to wait for on empty[s]: the first pass over the ring succeeds at once
+  auto advance = [&]() { if (++s == S) { s = 0; par ^= 1u; } };
   const uint32_t g_bytes = (uint32_t)(32 * c.bins * 4);
   for (;;) {
     int item = 0;
@@ -324,15 +332,14 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
     const int cnt = w.cnt[tile_id], start = w.start[tile_id];
     if (cnt == 0 && c.accumulate) continue;    // req=add and nothing to add
     {
-      const int s = m % kTbStages;
-      mbar_wait(&ctl->empty[s], (((uint32_t)m / kTbStages) & 1u) ^ 1u);
+      mbar_wait(&ctl->empty[s], par);
       if (lane == 0) {
         int* hd = reinterpret_cast<int*>(stages + (size_t)s * c.stage_bytes);
         hd[0] = cnt ? kMsgBegin : kMsgZero;
         reinterpret_cast<int4*>(hd)[1] = make_int4(l, b, cg * 32, ty0 | (tx0 << 16));
         mbar_arrive(&ctl->full[s]);
       }
-      ++m;
+      advance();
     }
     for (int base = 0; base < cnt; base += 32) {
       const int nb = min(32, cnt - base);
@@ -355,8 +362,7 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
           const int n1 = __shfl_sync(full, my_n, j + 1);
           if (lane < c.PW) xe = reinterpret_cast<const uint4*>(w.xtab + (size_t)n1 * c.tx)[lane];
         }
-        const int s = m % kTbStages;
-        mbar_wait(&ctl->empty[s], (((uint32_t)m / kTbStages) & 1u) ^ 1u);
+        mbar_wait(&ctl->empty[s], par);
         unsigned char* st = stages + (size_t)s * c.stage_bytes;
         const int ra = max(y0, ty0) - ty0;
         const int rb = min(y0 + Hf - 1, ty0 + v.th - 1) - ty0;
@@ -370,12 +376,11 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
           bulk_g2s(st + c.off_rt + ra * 32, w.rowtab + ((size_t)n * c.max_hf + (ra + ty0 - y0)) * 2, rt_bytes,
                    &ctl->full[s]);
         }
-        ++m;
+        advance();
       }
     }
   }
-  const int s = m % kTbStages;
-  mbar_wait(&ctl->empty[s], (((uint32_t)m / kTbStages) & 1u) ^ 1u);
+  mbar_wait(&ctl->empty[s], par);
   if (lane == 0) {
     reinterpret_cast<int*>(stages + (size_t)s * c.stage_bytes)[0] = kMsgStop;
     mbar_arrive(&ctl->full[s]);
@@ -393,28 +398,52 @@ __device__ __forceinline__ void tb_row(const float* __restrict__ gl, const uint2
   if (nph == 0) return;
   const float* gp = gl + (int)(q0.x & 0xffu) * PW;
   float h[PW];
+  // g[lane * bins + bin]: conflict-free 32-bit loads when bins is odd (7x7); for 14x14 (bins = 196, lane stride
+  // = 4 banks) 64-bit loads of bin pairs halve the 4-way conflicts (rows of PW = 14 floats are 8-byte aligned)
+  auto grow = [&](int k, float (&gv)[PW]) {
+    if constexpr ((PW & 1) == 0) {
+      const float2* g2 = reinterpret_cast<const float2*>(gp + k * PW);
+#pragma unroll
+      for (int j = 0; j < PW / 2; ++j) { const float2 v = g2[j]; gv[2 * j] = v.x; gv[2 * j + 1] = v.y; }
+    } else {
+#pragma unroll
+      for (int pw = 0; pw < PW; ++pw) gv[pw] = gp[k * PW + pw];
+    }
+  };
   {
     const float w0 = __uint_as_float(q0.y);
+    float gv[PW];
+    grow(0, gv);
 #pragma unroll
-    for (int pw = 0; pw < PW; ++pw) h[pw] = w0 * gp[pw];
+    for (int pw = 0; pw < PW; ++pw) h[pw] = w0 * gv[pw];
   }
   if (nph > 1) {
     const uint2 q1 = rt[1];                  // {w1, w2}
     const float w1 = __uint_as_float(q1.x);
+    {
+      float gv[PW];
+      grow(1, gv);
 #pragma unroll
-    for (int pw = 0; pw < PW; ++pw) h[pw] = fmaf(w1, gp[PW + pw], h[pw]);
+      for (int pw = 0; pw < PW; ++pw) h[pw] = fmaf(w1, gv[pw], h[pw]);
+    }
     if (nph > 2) {
       const float w2 = __uint_as_float(q1.y);
+      {
+        float gv[PW];
+        grow(2, gv);
 #pragma unroll
-      for (int pw = 0; pw < PW; ++pw) h[pw] = fmaf(w2, gp[2 * PW + pw], h[pw]);
+        for (int pw = 0; pw < PW; ++pw) h[pw] = fmaf(w2, gv[pw], h[pw]);
+      }
       if (nph > 3) {
         const uint4 q2 = reinterpret_cast<const uint4*>(rt)[1];   // {w3..w6}
         const float wk[4] = {__uint_as_float(q2.x), __uint_as_float(q2.y), __uint_as_float(q2.z), __uint_as_float(q2.w)};
 #pragma unroll
         for (int k = 3; k < 7; ++k) {
           if (k < nph) {
+            float gv[PW];
+            grow(k, gv);
 #pragma unroll
-            for (int pw = 0; pw < PW; ++pw) h[pw] = fmaf(wk[k - 3], gp[k * PW + pw], h[pw]);
+            for (int pw = 0; pw < PW; ++pw) h[pw] = fmaf(wk[k - 3], gv[pw], h[pw]);
           }
         }
       }
@@ -445,10 +474,10 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
   extern __shared__ __align__(128) unsigned char smem[];
   float* tile = reinterpret_cast<float*>(smem);
   unsigned char* stages = smem + c.tile_bytes;
-  TbCtl* ctl = reinterpret_cast<TbCtl*>(smem + c.tile_bytes + (size_t)kTbStages * c.stage_bytes);
+  TbCtl* ctl = reinterpret_cast<TbCtl*>(smem + c.tile_bytes + (size_t)c.n_stages * c.stage_bytes);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < kTbStages; ++s) {
+    for (int s = 0; s < c.n_stages; ++s) {
       mbar_init(&ctl->full[s], 1);
       mbar_init(&ctl->empty[s], kTbWarps);
     }
@@ -467,7 +496,8 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
   if (warp < c.max_rows)
     for (int i = lane; i < kTbRowWords; i += 32) trow[i] = 0.0f;
   __syncwarp();
-  int m = 0;
+  int s = 0;
+  uint32_t par = 0;
   bool have = false, touched = false;    // touched: some RoI of the item reached this warp's row
   int lvl = 0, img = 0, c0 = 0, ty0 = 0, tx0 = 0, th = 0, tw = 0, H = 0, W = 0;
   auto write_row = [&](bool zeros) {
@@ -505,8 +535,7 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
     __syncwarp();
   };
   for (;;) {
-    const int s = m % kTbStages;
-    mbar_wait(&ctl->full[s], ((uint32_t)m / kTbStages) & 1u);
+    mbar_wait(&ctl->full[s], par);
     const unsigned char* st = stages + (size_t)s * c.stage_bytes;
     const int hd = reinterpret_cast<const int*>(st)[0];
     const int kind = hd & 0xff;
@@ -530,7 +559,7 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&ctl->empty[s]);
-    ++m;
+    if (++s == c.n_stages) { s = 0; par ^= 1u; }
   }
 }
 
@@ -569,16 +598,19 @@ int tile_backward(const FpnDesc& d, const float* rois, const int* levels, const 
   MXD_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t zbytes = (size_t)((char*)w.start - (char*)w.hdr);    // hdr, cnt, cursor
   MXD_CUDA_OK(cudaMemsetAsync(w.hdr, 0, zbytes, st));
-  tplan_rois_kernel<<<(R * 32 + 255) / 256, 256, 0, st>>>(d, c, w, rois, levels, R);
+  if (PH == 7) tplan_rois_kernel<7><<<(R * 32 + 255) / 256, 256, 0, st>>>(d, c, w, rois, levels, R);
+  else tplan_rois_kernel<14><<<(R * 32 + 255) / 256, 256, 0, st>>>(d, c, w, rois, levels, R);
   MXD_POST_LAUNCH("roi_align_tplan_rois");
   tplan_group_kernel<<<1, 1024, 0, st>>>(c, w, R);
   MXD_POST_LAUNCH("roi_align_tplan_group");
   static bool attr_done = false;
   if (!attr_done) {
     MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_tile_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem));
+    MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_tile_bwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem));
     attr_done = true;
   }
-  roi_align_tile_bwd_kernel<7><<<sms, kTbThreads, c.smem_bytes, st>>>(d, c, w, gout);
+  if (PW == 7) roi_align_tile_bwd_kernel<7><<<sms, kTbThreads, c.smem_bytes, st>>>(d, c, w, gout);
+  else roi_align_tile_bwd_kernel<14><<<sms, kTbThreads, c.smem_bytes, st>>>(d, c, w, gout);
   MXD_POST_LAUNCH("roi_align_tile_bwd");
   tile_bwd_fallback_kernel<<<2 * sms, 256, 0, st>>>(d, c, w, rois, levels, const_cast<float*>(gout));
   MXD_POST_LAUNCH("roi_align_tile_bwd_fallback");

@@ -91,10 +91,11 @@ def test_roi_align_vs_oracle_random(sr, ps, roi_path):
     assert close(N(acc), base + gref, 1e-4)
 
 
+@pytest.mark.parametrize("PS", [7, 14])
 @pytest.mark.parametrize("C,H,W,R", [(32, 50, 68, 96), (64, 100, 168, 300), (32, 13, 9, 40), (96, 70, 130, 64)])
-def test_roi_align_tile_backward_paths(C, H, W, R):
-    """Tile-resident backward (C % 32 == 0, 7x7, sr 2): tiny / huge / out-of-image RoIs (those take the RED
-    fallback after the tiles are written), partial edge tiles, req=write and req=add."""
+def test_roi_align_tile_backward_paths(C, H, W, R, PS):
+    """Tile-resident backward (C % 32 == 0, 7x7 / 14x14, sr 2): tiny / huge / out-of-image RoIs (those take the
+    RED fallback after the tiles are written), partial edge tiles, req=write and req=add."""
     from mxdetection_b200.ops import roi_align_backward
     rng = np.random.default_rng(C + H + R)
     Nn = 2
@@ -105,19 +106,19 @@ def test_roi_align_tile_backward_paths(C, H, W, R):
     rois[1] = [1, 8, 8, 8.5, 8.5]                        # degenerate: every sample in one pixel quad
     rois[2] = [5, 0, 0, 10, 10]                          # bad batch index: no gradient
     rois[3] = [0, 4 * W - 6, 4 * H - 6, 4 * W - 1, 4 * H - 1]   # clamped at the far border
-    gout = rng.standard_normal((R, C, 7, 7)).astype(F)
+    gout = rng.standard_normal((R, C, PS, PS)).astype(F)
     shape = (Nn, C, H, W)
-    gref = cref.roi_align_backward(gout, rois, shape, (7, 7), 0.25, 2)
-    gin = N(roi_align_backward(T(gout), T(rois), shape, (7, 7), 0.25, 2))
+    gref = cref.roi_align_backward(gout, rois, shape, (PS, PS), 0.25, 2)
+    gin = N(roi_align_backward(T(gout), T(rois), shape, (PS, PS), 0.25, 2))
     assert close(gin, gref, 1e-4)
     base = rng.standard_normal(shape).astype(F)
     acc = T(base.copy())
-    roi_align_backward(T(gout), T(rois), shape, (7, 7), 0.25, 2, grad_data=acc, accumulate=True)
+    roi_align_backward(T(gout), T(rois), shape, (PS, PS), 0.25, 2, grad_data=acc, accumulate=True)
     assert close(N(acc), base + gref, 1e-4)
     # no RoI at all on image 1: its tiles are still zero-filled under req=write
     rois0 = rois.copy(); rois0[:, 0] = 0
-    g0 = N(roi_align_backward(T(gout), T(rois0), shape, (7, 7), 0.25, 2))
-    assert np.all(g0[1] == 0) and close(g0, cref.roi_align_backward(gout, rois0, shape, (7, 7), 0.25, 2), 1e-4)
+    g0 = N(roi_align_backward(T(gout), T(rois0), shape, (PS, PS), 0.25, 2))
+    assert np.all(g0[1] == 0) and close(g0, cref.roi_align_backward(gout, rois0, shape, (PS, PS), 0.25, 2), 1e-4)
 
 
 def test_roi_align_edge_cases(roi_path):
@@ -236,6 +237,11 @@ def test_mask_branch_cfg4_14x14():
     out = roi_align_fpn_forward([T(f) for f in d["feats"]], T(d["rois"]), (14, 14), d["scales"], 2, levels=T(lv))
     ref = cref.roi_align_forward(d["feats"], d["rois"], (14, 14), d["scales"], 2, lv)
     assert close(N(out), ref, 1e-5)
+    from mxdetection_b200.ops import roi_align_fpn_backward
+    g = roi_align_fpn_backward(T(d["grad_out"]), T(d["rois"]), [f.shape for f in d["feats"]], (14, 14), d["scales"], 2)
+    gref = cref.roi_align_backward(d["grad_out"], d["rois"], [f.shape for f in d["feats"]], (14, 14), d["scales"], 2, lv)
+    for a, b in zip(g, gref):
+        assert close(N(a), b, 1e-4)
 
 
 # ================================================================ top-k (Spec B/H) ==
