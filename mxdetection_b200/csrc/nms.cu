@@ -1,4 +1,4 @@
-// Hard NMS (Spec B): 64-bit suppression bitmask + single-warp greedy resolve.
+// Hard NMS (Spec B): 64-bit suppression bitmask + on-device greedy resolve.
 //
 // Contract: mx.nd.contrib.box_nms of mxnet 1.3.0 (module mxdetection/ops,
 // /root/reference/README.md:24): stable score-descending order, strict
@@ -7,11 +7,11 @@
 // Kernel 1 (mask): grid (col block, row block, segment), 64 threads.  Thread r
 //   of a row block tests its box against the 64 boxes of the column block held
 //   in shared memory and writes one u64 word.  Only the upper triangle runs.
-// Kernel 2 (resolve): one warp per segment.  For each block of 64 boxes the
-//   diagonal words are resolved sequentially with shuffles (all lanes track
-//   the same `cur` word), then the rows of the kept boxes are OR-ed into the
-//   per-lane remaining-suppression words; nothing leaves the device (MXNet's
-//   MultiProposal copies the mask to the host for this step).
+// Kernel 2 (resolve): one CTA of 8 warps per segment.  For each block of 64 boxes
+//   warp 0 resolves the diagonal words sequentially with shuffles (all lanes track
+//   the same `cur` word), then all warps OR the rows of the kept boxes into the
+//   remaining-suppression words; nothing leaves the device (MXNet's MultiProposal
+//   copies the mask to the host for this step).
 #include "internal.h"
 
 namespace mxd {

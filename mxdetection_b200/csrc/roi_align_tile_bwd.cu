@@ -7,7 +7,7 @@
 // caps an atomic scatter at ~0.5 ms on BASELINE config 3; shared-memory fp32 atomics are CAS
 // loops.  This kernel needs neither:
 //
-//  * every gradient map is cut into tiles of <= 31 rows x 48 columns x 32 channels that live in
+//  * every gradient map is cut into tiles of <= 25 (7x7) / 19 (14x14) rows x 48 columns x 32 channels that live in
 //    shared memory as [pixel][33 words] (channel innermost).  Lane = channel, so all 32 lanes of
 //    a warp run the same control flow with warp-uniform weights, and every shared-memory access
 //    is bank-conflict free;
@@ -16,8 +16,8 @@
 //  * the planner (one warp per RoI) turns Spec A's 2 x PH*sr row taps into a dense per-row
 //    table (first bin, up to 7 bin weights), lists the RoIs intersecting every tile, and packs
 //    the x taps; a producer warp streams, per (RoI, tile) pair, the RoI's 32-channel slice of
-//    grad_out (one TMA bulk copy, read as g[lane*bins + bin]: conflict free because bins is
-//    odd), the row-table slice and the tile-relative x taps through an mbarrier ring;
+//    grad_out (one TMA bulk copy, read as g[lane*bins + bin]: conflict free for 7x7 because bins is
+//    odd; 14x14 reads bin pairs), the row-table slice and the tile-relative x taps through an mbarrier ring;
 //  * each tile is written to HBM exactly once with plain coalesced stores (req=write needs no
 //    memset; req=add adds on the way out).
 //
@@ -84,8 +84,8 @@ static TWs carve_tile(void* base, int R, int NT, int tx, int max_hf) {
   return w;
 }
 
-// Host: tile geometry per level for the shared-memory budget.  Only the (7x7, sample_ratio 2)-shaped
-// instantiations exist; everything else keeps the RED kernels.
+// Host: tile geometry per level for the shared-memory budget.  7x7 and 14x14 at sample_ratio 2 with
+// C % 32 == 0 are instantiated; everything else keeps the RED kernels.
 static bool make_tcfg(int N, int C, int L, const int* Hs, const int* Ws, int PH, int PW, int sr, float finest,
                       int accumulate, TCfg* c) {
   if (sr != 2 || !((PH == 7 && PW == 7) || (PH == 14 && PW == 14)) || (C & 31) != 0 || C == 0) return false;
