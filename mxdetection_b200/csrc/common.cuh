@@ -77,6 +77,17 @@ inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Opt-in dynamic shared memory is a per-DEVICE function attribute: call sites set it once per device
+// (`static unsigned long long seen = 0; if (first_use_on_device(&seen)) cudaFuncSetAttribute(...)`).
+inline bool first_use_on_device(unsigned long long* seen) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*seen & bit) return false;
+  *seen |= bit;
+  return true;
+}
+
 // ---- device helpers -------------------------------------------------------------
 // float -> uint32 whose unsigned order equals the float order (-0 == +0).
 __device__ __forceinline__ uint32_t f32_orderable(float x) {

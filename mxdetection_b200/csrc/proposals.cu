@@ -221,11 +221,9 @@ int mxd_rpn_proposals(const DLTensor* const* scores, const DLTensor* const* delt
   c.L = L; c.kmax = km; c.keep_stride = ks; c.max_num = cfg->max_num;
   c.out = dptr<float>(proposals); c.num_valid = dptr<int>(num_valid);
   const int smem = MXD_SORT_CAP * (int)sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long seen = 0;
+  if (first_use_on_device(&seen))
     MXD_CUDA_OK(cudaFuncSetAttribute(rpn_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
   rpn_collect_kernel<<<B, kCollectThreads, smem, st>>>(c);
   MXD_POST_LAUNCH("rpn_collect");
   return MXD_OK;

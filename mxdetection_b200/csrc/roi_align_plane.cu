@@ -1152,13 +1152,12 @@ int plane_forward(const FpnDesc& d, const float* rois, const int* levels, float*
   if (stream) {
     plan_pack_kernel<<<(R * c.s4_ent + 255) / 256, 256, 0, st>>>(c, w, R);
     MXD_POST_LAUNCH("roi_align_plan_pack");
-    static bool attr4 = false;
-    if (!attr4) {
+    static unsigned long long seen4 = 0;
+    if (first_use_on_device(&seen4)) {
       MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_stream_fwd_kernel<7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemLimit));
       MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_stream_fwd_kernel<14, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemLimit));
-      attr4 = true;
     }
     if (PH == 7)
       roi_align_stream_fwd_kernel<7, 7><<<num_sms(), c.threads, c.smem_bytes, st>>>(d, c, w, rois, levels, out);
@@ -1171,12 +1170,10 @@ int plane_forward(const FpnDesc& d, const float* rois, const int* levels, float*
   const bool tap = sr == 2 && PH == 7 && PW == 7 && c.tab_bytes >= ((c.threads - 32) >> 5) * 128;
   auto kern = tap ? roi_align_plane_fwd_tap_kernel<7, 7>
                   : (sr == 2) ? roi_align_plane_fwd_kernel<2> : roi_align_plane_fwd_kernel<0>;
-  static int attr_done[3] = {0, 0, 0};
+  static unsigned long long seen[3] = {0, 0, 0};
   const int ki = tap ? 2 : sr == 2 ? 0 : 1;
-  if (attr_done[ki] < c.smem_bytes) {
+  if (first_use_on_device(&seen[ki]))
     MXD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_done[ki] = kSmemLimit;
-  }
   kern<<<num_sms() * c.ctas_per_sm, c.threads, c.smem_bytes, st>>>(d, c, w, rois, levels, out);
   MXD_POST_LAUNCH("roi_align_plane_fwd");
   *handled = 1;

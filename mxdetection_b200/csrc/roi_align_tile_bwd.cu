@@ -603,11 +603,10 @@ int tile_backward(const FpnDesc& d, const float* rois, const int* levels, const 
   MXD_POST_LAUNCH("roi_align_tplan_rois");
   tplan_group_kernel<<<1, 1024, 0, st>>>(c, w, R);
   MXD_POST_LAUNCH("roi_align_tplan_group");
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long seen = 0;
+  if (first_use_on_device(&seen)) {
     MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_tile_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem));
     MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_tile_bwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem));
-    attr_done = true;
   }
   if (PW == 7) roi_align_tile_bwd_kernel<7><<<sms, kTbThreads, c.smem_bytes, st>>>(d, c, w, gout);
   else roi_align_tile_bwd_kernel<14><<<sms, kTbThreads, c.smem_bytes, st>>>(d, c, w, gout);

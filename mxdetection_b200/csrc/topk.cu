@@ -450,12 +450,11 @@ int launch_topk(const TopkParams& p, cudaStream_t st) {
   }
   bool big = false;
   for (int l = 0; l < p.num_levels; ++l) big = big || p.n[l] > kCap;
-  static bool attr_set = false;
+  static unsigned long long seen = 0;
   const int smem = kCap * (int)sizeof(u64);
-  if (!attr_set) {
+  if (first_use_on_device(&seen)) {
     MXD_CUDA_OK(cudaFuncSetAttribute(topk_segment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     MXD_CUDA_OK(cudaFuncSetAttribute(topk_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * smem));
-    attr_set = true;
   }
   if (big && (long long)S * kTopkCluster < (1ll << 31)) {
     cudaLaunchConfig_t cfg = {};
