@@ -181,10 +181,11 @@ int launch_nms_sorted(const NmsSortedArgs& a, cudaStream_t st) {
     MXD_POST_LAUNCH("nms_mask");
   }
   const size_t smem = (size_t)(W > 0 ? W : 1) * (1 + 2 * 64) * sizeof(u64);
-  MXD_REQUIRE(smem <= 227 * 1024, MXD_ENOTSUP, "NMS segment of %d boxes exceeds the resolve kernel's shared memory", a.n_max);
+  constexpr int kResolveSmemMax = 226 * 1024;      // 227 KB per CTA minus the kernel's static shared variables
+  MXD_REQUIRE(smem <= (size_t)kResolveSmemMax, MXD_ENOTSUP, "NMS segment of %d boxes exceeds the resolve kernel's shared memory", a.n_max);
   static unsigned long long seen = 0;
   if (first_use_on_device(&seen))
-    MXD_CUDA_OK(cudaFuncSetAttribute(nms_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MXD_CUDA_OK(cudaFuncSetAttribute(nms_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResolveSmemMax));
   nms_resolve_kernel<<<a.S, kResolveThreads, smem, st>>>(a, W);
   MXD_POST_LAUNCH("nms_resolve");
   return MXD_OK;
