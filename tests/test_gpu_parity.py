@@ -121,6 +121,36 @@ def test_roi_align_tile_backward_paths(C, H, W, R, PS):
     assert np.all(g0[1] == 0) and close(g0, cref.roi_align_backward(gout, rois0, shape, (PS, PS), 0.25, 2), 1e-4)
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_roi_align_fpn_fuzz_shapes(seed):
+    """Random FPN geometries through the shipped fast paths (stream forward / tile backward) and their fallbacks:
+    odd and 4-aligned widths, 1-4 levels, 32-96 channels, 7x7 and 14x14, RoIs of every size incl. out of image."""
+    from mxdetection_b200.ops import roi_align_fpn_forward, roi_align_fpn_backward
+    rng = np.random.default_rng(900 + seed)
+    L_ = int(rng.integers(1, 5)); Nn = int(rng.integers(1, 4)); C = int(rng.choice([32, 64, 96]))
+    PS = int(rng.choice([7, 14]))
+    h0 = int(rng.integers(20, 140)); w0 = int(rng.integers(20, 180))
+    if seed % 2 == 0:
+        w0 = (w0 + 7) // 8 * 8                      # 16-byte aligned rows on the finest levels: TMA band path
+    shapes = [(Nn, C, max(2, -(-h0 // (1 << l))), max(2, -(-w0 // (1 << l)))) for l in range(L_)]
+    scales = [1.0 / (4 << l) for l in range(L_)]
+    feats = [rng.standard_normal(s).astype(F) for s in shapes]
+    R = int(rng.integers(1, 200))
+    img_h, img_w = 4 * h0, 4 * w0
+    x1 = rng.uniform(-20, img_w, R); y1 = rng.uniform(-20, img_h, R)
+    bw = np.exp(rng.uniform(np.log(2), np.log(1.2 * img_w), R)); bh = np.exp(rng.uniform(np.log(2), np.log(1.2 * img_h), R))
+    rois = np.stack([np.sort(rng.integers(0, Nn, R)), x1, y1, x1 + bw, y1 + bh], 1).astype(F)
+    lv = oracle.map_roi_levels(rois, L_) if L_ > 1 else None
+    out = roi_align_fpn_forward([T(f) for f in feats], T(rois), (PS, PS), scales, 2)
+    ref = cref.roi_align_forward(feats, rois, (PS, PS), scales, 2, lv)
+    assert close(N(out), ref, 1e-5)
+    gout = rng.standard_normal(ref.shape).astype(F)
+    g = roi_align_fpn_backward(T(gout), T(rois), shapes, (PS, PS), scales, 2)
+    gref = cref.roi_align_backward(gout, rois, shapes, (PS, PS), scales, 2, lv)
+    for a, b in zip(g, gref):
+        assert close(N(a), b, 1e-4)
+
+
 def test_roi_align_edge_cases(roi_path):
     from mxdetection_b200.ops import roi_align_forward, roi_align_backward
     data = np.random.default_rng(0).standard_normal((2, 3, 10, 12)).astype(F)
