@@ -57,6 +57,29 @@ def measured_peaks():
 CURRENT_NCU_SUMMARY = "ncu_r1i.txt"     # `ncu --set full` capture of the kernels this tree ships (profiles/README.md)
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-rank runs: keep this rank's threads (and therefore its first-touch pinned host buffers of the e2e leg)
+    on the NUMA node the GPU hangs off, so eight ranks do not pull their PCIe traffic across the socket link.
+    Best effort - silently skipped when sysfs does not say."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            sys.stderr.write("[bench] gpu %d (%s): bound to NUMA node %d, %d cpus\n" % (index, bus, node, len(cpus)))
+    except Exception as e:
+        sys.stderr.write("[bench] gpu %d: NUMA binding skipped (%r)\n" % (index, e))
+
+
 def ncu_traffic(kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
     `ncu --set full` summary under profiles/ (profiles/summarize.py writes them); None when there is none."""
@@ -221,6 +244,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
     torch.cuda.set_device(local)
+    if world > 1:
+        bind_to_gpu_numa_node(local)
     dev = torch.device("cuda", local)
     if world > 1:
         # NCCL prints its version banner to STDOUT when the communicator is created; the contract is ONE json
