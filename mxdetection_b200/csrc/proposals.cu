@@ -34,7 +34,10 @@ __global__ void __launch_bounds__(kCollectThreads, 1) rpn_collect_kernel(Collect
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sc = reinterpret_cast<float*>(smem_raw);     // concatenated kept scores (<= MXD_SORT_CAP)
   __shared__ int s_off[MXD_MAX_LEVELS + 1];
+  // grid (B, parts): every CTA loads the image's kept scores (the binary searches need all lists) and ranks
+  // a 1/parts share of the candidates - the ranking is a chain of dependent shared-memory reads
   const int b = blockIdx.x, tid = threadIdx.x;
+  const int part = blockIdx.y, nparts = gridDim.y;
   if (tid == 0) {
     int acc = 0;
     for (int l = 0; l < a.L; ++l) {
@@ -52,12 +55,14 @@ __global__ void __launch_bounds__(kCollectThreads, 1) rpn_collect_kernel(Collect
     for (int j = tid; j < cnt; j += kCollectThreads)
       sc[s_off[l] + j] = a.vals[(size_t)s * a.kmax + a.keep[(size_t)s * a.keep_stride + j]] + 0.0f;   // -0 -> +0
   }
-  for (int r = nout + tid; r < a.max_num; r += kCollectThreads) {
-    float* o = out + (size_t)r * 5;
-    o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
+  if (part == 0) {
+    for (int r = nout + tid; r < a.max_num; r += kCollectThreads) {
+      float* o = out + (size_t)r * 5;
+      o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
+    }
   }
   __syncthreads();
-  for (int ci = tid; ci < total; ci += kCollectThreads) {
+  for (int ci = part * kCollectThreads + tid; ci < total; ci += kCollectThreads * nparts) {
     int l = 0;
     while (l + 1 < a.L && ci >= s_off[l + 1]) ++l;
     const float v = sc[ci];
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(kCollectThreads, 1) rpn_collect_kernel(Collect
       o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = a.vals[(size_t)s * a.kmax + pos];
     }
   }
-  if (tid == 0) a.num_valid[b] = nout;
+  if (tid == 0 && part == 0) a.num_valid[b] = nout;
 }
 
 struct RpnWs {
@@ -224,7 +229,7 @@ int mxd_rpn_proposals(const DLTensor* const* scores, const DLTensor* const* delt
   static unsigned long long seen = 0;
   if (first_use_on_device(&seen))
     MXD_CUDA_OK(cudaFuncSetAttribute(rpn_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  rpn_collect_kernel<<<B, kCollectThreads, smem, st>>>(c);
+  rpn_collect_kernel<<<dim3(B, 4), kCollectThreads, smem, st>>>(c);
   MXD_POST_LAUNCH("rpn_collect");
   return MXD_OK;
 }
