@@ -18,26 +18,33 @@ namespace mxd {
 
 typedef unsigned long long u64;
 
-__global__ void __launch_bounds__(64) nms_mask_kernel(NmsSortedArgs a, int W) {
-  const int cb = blockIdx.x, rb = blockIdx.y, s = blockIdx.z;
-  if (cb < rb) return;
+// grid (column block, group of 4 row blocks, segment), 256 threads: the 64 boxes of the column block are staged
+// once for four row blocks (64-thread CTAs spent most of their short life on that load).
+constexpr int kMaskRowBlocks = 4;
+
+__global__ void __launch_bounds__(64 * kMaskRowBlocks) nms_mask_kernel(NmsSortedArgs a, int W) {
+  const int cb = blockIdx.x, rb0 = blockIdx.y * kMaskRowBlocks, s = blockIdx.z;
+  if (cb < rb0) return;                                    // the whole CTA lies below the diagonal
   const int n = a.counts ? min(a.counts[s], a.n_max) : a.n_max;
-  if (rb * 64 >= n || cb * 64 >= n) return;
+  if (rb0 * 64 >= n || cb * 64 >= n) return;
   const size_t seg = (size_t)s * a.stride;
   __shared__ float4 sb[64];
   __shared__ float sa[64];
   __shared__ int sid[64];
-  const int t = threadIdx.x;
-  const int c = cb * 64 + t;
-  if (c < n) {
-    float4 b = a.boxes[seg + c];
-    sb[t] = b;
-    sa[t] = box_area_clamped(b.x, b.y, b.z, b.w, a.delta);
-    sid[t] = a.ids ? a.ids[seg + c] : 0;
+  const int t = threadIdx.x & 63;
+  const int rb = rb0 + (threadIdx.x >> 6);
+  if (threadIdx.x < 64) {
+    const int c = cb * 64 + t;
+    if (c < n) {
+      float4 b = a.boxes[seg + c];
+      sb[t] = b;
+      sa[t] = box_area_clamped(b.x, b.y, b.z, b.w, a.delta);
+      sid[t] = a.ids ? a.ids[seg + c] : 0;
+    }
   }
   __syncthreads();
   const int r = rb * 64 + t;
-  if (r >= n) return;
+  if (rb > cb || r >= n) return;                          // only the upper triangle is ever read
   const float4 me = a.boxes[seg + r];
   const float area = box_area_clamped(me.x, me.y, me.z, me.w, a.delta);
   const int myid = a.ids ? a.ids[seg + r] : 0;
@@ -176,8 +183,8 @@ int launch_nms_sorted(const NmsSortedArgs& a, cudaStream_t st) {
   const int W = (a.n_max + 63) / 64;
   if (a.n_max > 0) {
     MXD_REQUIRE(a.S <= 65535 && W <= 65535, MXD_ENOTSUP, "too many NMS segments");
-    dim3 grid(W, W, a.S);
-    nms_mask_kernel<<<grid, 64, 0, st>>>(a, W);
+    dim3 grid(W, (W + kMaskRowBlocks - 1) / kMaskRowBlocks, a.S);
+    nms_mask_kernel<<<grid, 64 * kMaskRowBlocks, 0, st>>>(a, W);
     MXD_POST_LAUNCH("nms_mask");
   }
   const size_t smem = (size_t)(W > 0 ? W : 1) * (1 + 2 * 64) * sizeof(u64);
