@@ -76,6 +76,26 @@ __global__ void __launch_bounds__(kAssignThreads) assign_pass1_kernel(AssignArgs
     best[q] = (posa[q] && G > 0) ? 0.0f : -INFINITY;
     arg[q] = 0;
   }
+  // bounding box of the warp's active, positive-area anchors; `wall` = some active anchor has a non-positive
+  // (or NaN) area, whose 0/0 cases must reach the exact expression for every GT
+  const int lane = threadIdx.x & 31;
+  float4 wbox = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+  bool wall = false;
+#pragma unroll
+  for (int q = 0; q < A; ++q) {
+    if (!act[q]) continue;
+    if (!posa[q]) { wall = true; continue; }
+    wbox.x = fminf(wbox.x, me[q].x); wbox.y = fminf(wbox.y, me[q].y);
+    wbox.z = fmaxf(wbox.z, me[q].z); wbox.w = fmaxf(wbox.w, me[q].w);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    wbox.x = fminf(wbox.x, __shfl_xor_sync(0xffffffffu, wbox.x, o));
+    wbox.y = fminf(wbox.y, __shfl_xor_sync(0xffffffffu, wbox.y, o));
+    wbox.z = fmaxf(wbox.z, __shfl_xor_sync(0xffffffffu, wbox.z, o));
+    wbox.w = fmaxf(wbox.w, __shfl_xor_sync(0xffffffffu, wbox.w, o));
+  }
+  wall = __any_sync(0xffffffffu, wall);
   for (int g0 = 0; g0 < G; g0 += kGtChunk) {
     const int gc = min(kGtChunk, G - g0);
     __syncthreads();
@@ -92,36 +112,42 @@ __global__ void __launch_bounds__(kAssignThreads) assign_pass1_kernel(AssignArgs
                              : make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY);
     }
     __syncthreads();
-    for (int i = 0; i < gc; ++i) {
-      // Most (anchor, GT) pairs do not intersect: their IoU is +0 without the IEEE division (when the
-      // union is positive) and cannot raise gt_max.  Four compares per anchor prove it for a whole warp
-      // (128 anchors) at a time; only warps with a possible intersection run the exact expression.
-      const float4 rj = s_rej[i];
-      bool maybe = false;
-#pragma unroll
-      for (int q = 0; q < A; ++q)
-        maybe = maybe || (act[q] && (!posa[q] || !(me[q].z < rj.x || me[q].x > rj.z || me[q].w < rj.y || me[q].y > rj.w)));
-      if (!__any_sync(0xffffffffu, maybe)) continue;
-      const float4 g = s_gt[i];
-      const float ga = s_area[i];
-      unsigned bits = 0u;
-      bool any_hit = false;
-#pragma unroll
-      for (int q = 0; q < A; ++q) {
-        if (!act[q]) continue;
-        const float iw = __fadd_rn(__fsub_rn(fminf(me[q].z, g.z), fmaxf(me[q].x, g.x)), a.delta);
-        const float ih = __fadd_rn(__fsub_rn(fminf(me[q].w, g.w), fmaxf(me[q].y, g.y)), a.delta);
-        const bool hit = iw > 0.0f && ih > 0.0f;
-        float iou = 0.0f;
-        if (hit || !(__fadd_rn(ga, area[q]) > 0.0f)) iou = iou_spec_d(me[q], area[q], g, ga, a.delta);
-        if (iou > best[q]) { best[q] = iou; arg[q] = g0 + i; }   // strict > keeps the lowest g on ties
-        any_hit = any_hit || hit;
-        // NaN / negative IoU (degenerate boxes) never feed gt_max: see DESIGN.md
-        if (iou > 0.0f) bits = max(bits, __float_as_uint(iou));
+    // Most (anchor, GT) pairs do not intersect: their IoU is +0 without the IEEE division (when the union
+    // is positive) and cannot raise gt_max.  The warp's 128 anchors have one bounding box; 32 GT windows
+    // are tested against it per ballot, and only the surviving GTs (ascending, so ties keep the lowest g)
+    // run the exact expression.
+    for (int j0 = 0; j0 < gc; j0 += 32) {
+      const int gi = j0 + lane;
+      bool cand = false;
+      if (gi < gc) {
+        const float4 rj = s_rej[gi];
+        cand = wall || !(wbox.z < rj.x || wbox.x > rj.z || wbox.w < rj.y || wbox.y > rj.w);
       }
-      if (__any_sync(0xffffffffu, any_hit)) {
-        const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
-        if (wmax != 0u && (threadIdx.x & 31) == 0) atomicMax(&s_max[i], wmax);
+      unsigned cmask = __ballot_sync(0xffffffffu, cand);
+      while (cmask) {
+        const int i = j0 + __ffs(cmask) - 1;
+        cmask &= cmask - 1;
+        const float4 g = s_gt[i];
+        const float ga = s_area[i];
+        unsigned bits = 0u;
+        bool any_hit = false;
+#pragma unroll
+        for (int q = 0; q < A; ++q) {
+          if (!act[q]) continue;
+          const float iw = __fadd_rn(__fsub_rn(fminf(me[q].z, g.z), fmaxf(me[q].x, g.x)), a.delta);
+          const float ih = __fadd_rn(__fsub_rn(fminf(me[q].w, g.w), fmaxf(me[q].y, g.y)), a.delta);
+          const bool hit = iw > 0.0f && ih > 0.0f;
+          float iou = 0.0f;
+          if (hit || !(__fadd_rn(ga, area[q]) > 0.0f)) iou = iou_spec_d(me[q], area[q], g, ga, a.delta);
+          if (iou > best[q]) { best[q] = iou; arg[q] = g0 + i; }   // strict > keeps the lowest g on ties
+          any_hit = any_hit || hit;
+          // NaN / negative IoU (degenerate boxes) never feed gt_max: see DESIGN.md
+          if (iou > 0.0f) bits = max(bits, __float_as_uint(iou));
+        }
+        if (__any_sync(0xffffffffu, any_hit)) {
+          const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
+          if (wmax != 0u && lane == 0) atomicMax(&s_max[i], wmax);
+        }
       }
     }
     __syncthreads();
