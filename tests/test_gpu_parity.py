@@ -315,7 +315,8 @@ def test_nms_golden(golden_dir, name):
     assert np.array_equal(N(keep)[:k], g["keep"]) and np.all(N(keep)[k:] == -1)
 
 
-@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 128, 1000, 2000, 4100])
+# 7000 boxes: four-buffer band ring of the scan kernel; 8192 (the in-CTA sort capacity): three buffers
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 128, 129, 1000, 2000, 4100, 7000, 8192])
 @pytest.mark.parametrize("delta", [0.0, 1.0])
 def test_nms_vs_oracle_bit_exact(n, delta):
     from mxdetection_b200.ops import nms_indices
