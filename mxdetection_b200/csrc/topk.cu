@@ -38,53 +38,76 @@ __device__ __forceinline__ u64 make_key(float s, int i, int n, float valid_thres
   return ((u64)f32_orderable(s) << 32) | (u64)(uint32_t)(n - 1 - i);
 }
 
-// Warp 0 walks the 2048-bin histogram from the top and records the bin that holds the need-th largest key:
-// s_state = {bin, keys still needed inside it, keys in it}.
+// Finds the bin that holds the need-th largest key, walking the 2048-bin histogram from the top with the whole
+// CTA: thread t owns bins 2047-2t and 2046-2t, a warp scan plus a scan of the 32 warp totals gives every thread
+// the count above its bins.  s_state = {bin, keys still needed inside it, keys in it}.  (One warp walking 64 bins
+// per lane serially cost ~2 us per radix pass.)
+static_assert(kRadixBins == 2 * kTopkThreads, "two bins per thread");
 __device__ __forceinline__ void radix_find_bin(const unsigned int* hist, int need, u64* s_state) {
-  if (threadIdx.x < 32) {
-    // lane L owns bins [hi-63, hi] with hi = 2047 - 64*L (descending walk)
-    const int lane = threadIdx.x;
-    const int hi = kRadixBins - 1 - 64 * lane;
-    unsigned sum = 0;
-    for (int b = 0; b < 64; ++b) sum += hist[hi - b];
-    unsigned incl = sum;
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
+  __shared__ unsigned s_wsum[32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int b0 = kRadixBins - 1 - 2 * t;
+  const unsigned c0 = hist[b0], c1 = hist[b0 - 1];
+  const unsigned sum = c0 + c1;
+  unsigned incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  unsigned wincl = s_wsum[lane];
+  const unsigned wown = wincl;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, wincl, o);
+    if (lane >= o) wincl += v;
+  }
+  const unsigned base = __shfl_sync(0xffffffffu, wincl - wown, warp);
+  unsigned run = base + incl - sum;           // keys in the bins above mine
+  if (run < (unsigned)need && run + c0 >= (unsigned)need) {
+    s_state[0] = (u64)b0; s_state[1] = (u64)(need - run); s_state[2] = (u64)c0;
+  } else {
+    run += c0;
+    if (run < (unsigned)need && run + c1 >= (unsigned)need) {
+      s_state[0] = (u64)(b0 - 1); s_state[1] = (u64)(need - run); s_state[2] = (u64)c1;
     }
-    const unsigned excl = incl - sum;
-    if (excl < (unsigned)need && incl >= (unsigned)need) {
-      unsigned run = excl;
-      for (int b = 0; b < 64; ++b) {
-        unsigned h = hist[hi - b];
-        if (run + h >= (unsigned)need) {
-          s_state[0] = (u64)(hi - b);
-          s_state[1] = (u64)(need - run);   // still needed inside this bin
-          s_state[2] = (u64)h;
-          break;
-        }
-        run += h;
-      }
-    }
+  }
+}
+
+// Histogram vote of one warp: when every active lane holds the same digit (the top bits of the surviving scores
+// nearly always agree) ONE atomic carries the count - 32 same-address shared atomics serialise otherwise.
+__device__ __forceinline__ void radix_vote(unsigned int* hist, bool act, unsigned d) {
+  const unsigned am = __ballot_sync(0xffffffffu, act);
+  if (am == 0u) return;
+  const int leader = __ffs(am) - 1;
+  const unsigned d0 = __shfl_sync(0xffffffffu, d, leader);
+  const unsigned same = __ballot_sync(0xffffffffu, act && d == d0);
+  if (same == am) {
+    if ((int)(threadIdx.x & 31) == leader) atomicAdd(&hist[d0], (unsigned)__popc(am));
+  } else if (act) {
+    atomicAdd(&hist[d], 1u);
   }
 }
 
 // k-th largest of cnt DISTINCT non-zero 64-bit keys held in shared memory (1 <= k <= cnt): MSB-first 11-bit
 // radix passes over a shared-memory histogram.  Far fewer instructions than sorting when only the threshold is
 // needed (a 4096-key bitonic sort costs ~4 k instructions per warp).  Returns T: exactly k keys are >= T.
-__device__ u64 radix_select_smem(const u64* src, int cnt, int k, unsigned int* hist, u64* s_state) {
+__device__ u64 radix_select_smem(const u64* src, int cnt, int k, unsigned int* hist, u64* s_state, int max_passes = 64) {
   u64 prefix = 0, pmask = 0;
   int need = k;
   int pos = 64;
-  while (pos > 0) {
+  while (pos > 0 && max_passes-- > 0) {
     const int width = pos < kRadixBits ? pos : kRadixBits;
     const int shift = pos - width;
     const u64 dmask = (1ull << width) - 1;
     for (int i = threadIdx.x; i < kRadixBins; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const u64 key = src[i];
-      if (key != 0 && (key & pmask) == prefix) atomicAdd(&hist[(unsigned)((key >> shift) & dmask)], 1u);
+    for (int i0 = 0; i0 < cnt; i0 += blockDim.x) {          // warp-uniform trip count: radix_vote is collective
+      const int i = i0 + threadIdx.x;
+      const u64 key = i < cnt ? src[i] : 0ull;
+      radix_vote(hist, key != 0 && (key & pmask) == prefix, (unsigned)((key >> shift) & dmask));
     }
     __syncthreads();
     radix_find_bin(hist, need, s_state);
@@ -98,11 +121,11 @@ __device__ u64 radix_select_smem(const u64* src, int cnt, int k, unsigned int* h
     __syncthreads();
     if (binsz == need) break;  // the whole bin is selected
   }
-  return prefix;
+  return prefix;  // max_passes reached: a lower bound (at least k keys are >= prefix)
 }
 
-// Lower bound on the k-th largest key of the segment: the k-th largest of the G group maxima (every group
-// maximum is a key of the segment, so at least k keys are >= it).  Fewer than k non-zero maxima: take every
+// Lower bound on the k-th largest key of the segment: (a lower bound of) the k-th largest of the G group maxima
+// (every group maximum is a key of the segment, so at least k keys are >= it).  Fewer than k non-zero maxima: take every
 // valid key (bound 1).
 __device__ u64 select_bound(const u64* maxima, int G, int k, unsigned int* hist, u64* s_state) {
   __shared__ int s_nz;
@@ -114,7 +137,9 @@ __device__ u64 select_bound(const u64* maxima, int G, int k, unsigned int* hist,
   if ((threadIdx.x & 31) == 0 && nz) atomicAdd(&s_nz, nz);
   __syncthreads();
   if (s_nz < k) return 1ull;
-  return radix_select_smem(maxima, G, k, hist, s_state);
+  // a bound, not the exact k-th maximum: two passes fix sign, exponent and 13 mantissa bits of the score - the
+  // keys that slip in below the exact value are a 2^-13 relative sliver of the score range
+  return radix_select_smem(maxima, G, k, hist, s_state, 2);
 }
 
 // Exact selection of the k-th largest key by MSB-first radix passes (slow path).
