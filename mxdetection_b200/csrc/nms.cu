@@ -23,6 +23,7 @@ typedef unsigned long long u64;
 // once for four row blocks (64-thread CTAs spent most of their short life on that load).
 constexpr int kMaskRowBlocks = 4;
 
+template <bool IDS>
 __global__ void __launch_bounds__(64 * kMaskRowBlocks) nms_mask_kernel(NmsSortedArgs a, int W, int bandmajor) {
   const int cb = blockIdx.x, rb0 = blockIdx.y * kMaskRowBlocks, s = blockIdx.z;
   if (cb < rb0) return;                                    // the whole CTA lies below the diagonal
@@ -36,12 +37,16 @@ __global__ void __launch_bounds__(64 * kMaskRowBlocks) nms_mask_kernel(NmsSorted
   const int rb = rb0 + (threadIdx.x >> 6);
   if (threadIdx.x < 64) {
     const int c = cb * 64 + t;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ar = 0.0f;
+    int id = 0;
     if (c < n) {
-      float4 b = a.boxes[seg + c];
-      sb[t] = b;
-      sa[t] = box_area_clamped(b.x, b.y, b.z, b.w, a.delta);
-      sid[t] = a.ids ? a.ids[seg + c] : 0;
+      b = a.boxes[seg + c];
+      ar = box_area_clamped(b.x, b.y, b.z, b.w, a.delta);
+      if (IDS) id = a.ids[seg + c];
     }
+    sb[t] = b; sa[t] = ar;
+    if (IDS) sid[t] = id;
   }
   __syncthreads();
   const int r = rb * 64 + t;
@@ -50,11 +55,13 @@ __global__ void __launch_bounds__(64 * kMaskRowBlocks) nms_mask_kernel(NmsSorted
   if (live) {
     const float4 me = a.boxes[seg + r];
     const float area = box_area_clamped(me.x, me.y, me.z, me.w, a.delta);
-    const int myid = a.ids ? a.ids[seg + r] : 0;
+    const int myid = IDS ? a.ids[seg + r] : 0;
     const int ncol = min(64, n - cb * 64);
     const int start = (cb == rb) ? t + 1 : 0;  // strictly later boxes only
+    // (a fully unrolled, predicated version of this loop measured 50 us against 40 us: the early exits of
+    // box_iou_gt on disjoint pairs are worth more than the loop overhead)
     for (int i = start; i < ncol; ++i) {
-      if (sid[i] != myid) continue;
+      if (IDS && sid[i] != myid) continue;
       if (box_iou_gt(me, area, sb[i], sa[i], a.delta, a.thr)) bits |= 1ull << i;
     }
   }
@@ -374,7 +381,8 @@ int launch_nms_sorted(const NmsSortedArgs& a, cudaStream_t st) {
   if (a.n_max > 0) {
     MXD_REQUIRE(a.S <= 65535 && W <= 65535, MXD_ENOTSUP, "too many NMS segments");
     dim3 grid(W, (W + kMaskRowBlocks - 1) / kMaskRowBlocks, a.S);
-    nms_mask_kernel<<<grid, 64 * kMaskRowBlocks, 0, st>>>(a, W, slots ? 1 : 0);
+    if (a.ids) nms_mask_kernel<true><<<grid, 64 * kMaskRowBlocks, 0, st>>>(a, W, slots ? 1 : 0);
+    else nms_mask_kernel<false><<<grid, 64 * kMaskRowBlocks, 0, st>>>(a, W, slots ? 1 : 0);
     MXD_POST_LAUNCH("nms_mask");
   }
   static unsigned long long seen = 0;
