@@ -275,7 +275,9 @@ def test_mask_branch_cfg4_14x14():
 
 
 # ================================================================ top-k (Spec B/H) ==
-@pytest.mark.parametrize("n,k", [(1, 1), (5, 10), (63, 7), (2048, 2048), (8192, 2000), (8193, 2000), (50000, 2000),
+# (40,40) .. (130,130): the sort's register phase alone / plus one and two shared-memory merge sizes; (8192,8192): full capacity
+@pytest.mark.parametrize("n,k", [(1, 1), (5, 10), (63, 7), (40, 40), (64, 64), (100, 100), (130, 130), (2048, 2048),
+                                  (8192, 2000), (8192, 8192), (8193, 2000), (50000, 2000),
                                   (217413, 2000), (201600, 6000), (300000, 1)])
 def test_topk_stable_bit_exact(n, k):
     from mxdetection_b200.ops import topk_stable
@@ -329,6 +331,21 @@ def test_nms_vs_oracle_bit_exact(n, delta):
     ref = oracle.nms(boxes, scores, 0.7, delta=delta)
     keep, num = nms_indices(T(boxes), T(scores), 0.7, delta=delta)
     assert int(num.item()) == len(ref) and np.array_equal(N(keep)[: len(ref)], ref)
+
+
+def test_nms_dependency_chains():
+    """Worst case of the scan kernel's fixed point: every box overlaps only its neighbours, so whether box i survives
+    depends on box i-1, ... all the way down (64 rounds per block), across block boundaries, with ties."""
+    from mxdetection_b200.ops import nms_indices
+    for n, step in ((64, 10.0), (200, 10.0), (1000, 7.0), (333, 12.0)):
+        x = np.arange(n, dtype=np.float64) * step
+        boxes = np.stack([x, np.zeros(n), x + 15.0, np.full(n, 10.0)], 1).astype(F)
+        for scores in (np.linspace(1, 0.1, n).astype(F),            # left to right
+                       np.linspace(0.1, 1, n).astype(F),             # right to left
+                       np.full(n, 0.5, F)):                          # all ties: index order
+            ref = oracle.nms(boxes, scores, 0.1, delta=0.0)
+            keep, num = nms_indices(T(boxes), T(scores), 0.1, delta=0.0)
+            assert int(num.item()) == len(ref) and np.array_equal(N(keep)[: len(ref)], ref), (n, step)
 
 
 def test_nms_options_topk_validthresh_ids_maxout():
