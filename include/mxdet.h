@@ -155,6 +155,24 @@ int mxd_max_iou_assign(const DLTensor* anchors, const DLTensor* gts, const DLTen
                        float pos_iou_thr, float neg_iou_thr, float min_pos_iou, float delta,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- N1  random sampling + target packing  (SURVEY.md 8(f) "next" row N1: mxdetection/core/anchor + core/bbox,
+ *      /root/reference/README.md:16-17; RandomSampler / anchor_target_single / bbox_target_single of mmdet 0.5).
+ *      RNG contract: keys (N) f32 in [0,1) are supplied by the caller; the sample is the positives (assigned > 0) /
+ *      negatives (assigned == 0) with the LARGEST keys, ties to the lower index.  kp = min(int(num*pos_fraction), N)
+ *      positives at most, negatives fill up to num (at most neg_pos_ub * max(1, num_pos) when neg_pos_ub >= 0).
+ *      pos_inds (kp) / neg_inds (min(num, N)) i32, -1 padded; counts (2) i32 = {num_pos, num_neg}.            */
+size_t mxd_random_sample_workspace_bytes(long long n, int num);
+int mxd_random_sample(const DLTensor* assigned, const DLTensor* keys, int num, float pos_fraction, int neg_pos_ub,
+                      DLTensor* pos_inds, DLTensor* neg_inds, DLTensor* counts, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* labels (N) i32, label_weights (N) f32, bbox_targets (N,4), bbox_weights (N,4): zero everywhere except the sampled
+ * rows - positives: label 1 (or gt_labels[g]), weight pos_weight (<= 0: 1), Spec F deltas to their GT, box weight 1;
+ * negatives: label weight 1.  gt_labels (G) i32 or NULL.                                                      */
+int mxd_pack_targets(const DLTensor* anchors, const DLTensor* assigned, const DLTensor* gts, const DLTensor* gt_labels,
+                     const DLTensor* pos_inds, const DLTensor* neg_inds, const float* means, const float* stds,
+                     float pos_weight, DLTensor* labels, DLTensor* label_weights, DLTensor* bbox_targets,
+                     DLTensor* bbox_weights, void* stream);
+
 /* ---- F1/F2  delta encode / decode + clip  (mxdetection/core/bbox,
  *      /root/reference/README.md:17; bbox2delta / delta2bbox of mmdet 0.5;
  *      Spec F).  means/stds: host float[4].  exp/log correctly rounded fp32.   */

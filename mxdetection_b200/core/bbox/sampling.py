@@ -4,13 +4,13 @@ anchor_target / bbox_target roles of mxdetection/core/anchor and core/bbox, /roo
 Device RNG contract (the reference's NumPy ``random.choice`` cannot be reproduced on a device, so the contract is
 stated instead): every candidate i gets a key u_i in [0,1) (``torch.rand`` of a caller-seeded generator, or keys
 passed in); the sampled positives are the positives with the LARGEST keys (ties -> lower index), likewise the
-negatives.  Given the same keys the CPU oracle returns identical index lists.  Selection runs on the library's
-stable top-k kernel; nothing synchronises with the host (fixed-capacity outputs, -1 padded, device counts)."""
+negatives.  Given the same keys the CPU oracle returns identical index lists.  Both calls are native
+(``mxd_random_sample``: key masking + one two-segment stable top-k + a finalising CTA; ``mxd_pack_targets``: memsets +
+one scatter kernel with the Spec F encoder); nothing synchronises with the host (fixed-capacity outputs, -1 padded,
+device counts)."""
 import torch
 
 from ... import _lib as L
-from ...ops.nms import topk_stable
-from .transforms import bbox2delta
 
 
 class SamplingResult:
@@ -29,26 +29,21 @@ class RandomSampler:
 
     def sample(self, assigned_gt_inds, keys=None, generator=None):
         L.require_cuda(assigned_gt_inds, keys)
-        a = assigned_gt_inds
+        a = assigned_gt_inds.to(torch.int32).contiguous()
         n = a.shape[0]
+        dev = a.device
         if keys is None:
-            keys = torch.rand(n, device=a.device, generator=generator)
-        keys = keys.float()
+            keys = torch.rand(n, device=dev, generator=generator)
+        keys = keys.float().contiguous()
         kp = min(int(self.num * self.pos_fraction), n)
         kn = min(self.num, n)
-        minus = torch.full_like(keys, -1.0)
-        pos_idx, pos_val = topk_stable(torch.where(a > 0, keys, minus), kp) if kp > 0 else (a.new_zeros(0), keys.new_zeros(0))
-        neg_idx, neg_val = topk_stable(torch.where(a == 0, keys, minus), kn) if kn > 0 else (a.new_zeros(0), keys.new_zeros(0))
-        pos_ok = pos_val >= 0
-        num_pos = pos_ok.sum(dtype=torch.int32).reshape(1)
-        quota = self.num - num_pos
-        if self.neg_pos_ub >= 0:
-            quota = torch.minimum(quota, (self.neg_pos_ub * torch.clamp(num_pos, min=1)).to(torch.int32))
-        neg_ok = (neg_val >= 0) & (torch.arange(kn, device=a.device, dtype=torch.int32) < quota)
-        num_neg = neg_ok.sum(dtype=torch.int32).reshape(1)
-        neg1 = torch.full_like(neg_idx, -1)
-        return SamplingResult(torch.where(pos_ok, pos_idx, torch.full_like(pos_idx, -1)), num_pos,
-                              torch.where(neg_ok, neg_idx, neg1), num_neg)
+        pos = torch.empty(kp, dtype=torch.int32, device=dev)
+        neg = torch.empty(kn, dtype=torch.int32, device=dev)
+        counts = torch.empty(2, dtype=torch.int32, device=dev)
+        ws = L.workspace(L.lib.mxd_random_sample_workspace_bytes(n, self.num), dev, "sample")
+        L.call("mxd_random_sample", L.dl(a), L.dl(keys), self.num, self.pos_fraction, int(self.neg_pos_ub), L.dl(pos),
+               L.dl(neg), L.dl(counts), ws.data_ptr(), ws.numel(), L.current_stream(dev))
+        return SamplingResult(pos, counts[0:1], neg, counts[1:2])
 
 
 def pack_targets(anchors, assigned_gt_inds, gt_bboxes, sampling, gt_labels=None, means=(0, 0, 0, 0), stds=(1, 1, 1, 1),
@@ -58,25 +53,14 @@ def pack_targets(anchors, assigned_gt_inds, gt_bboxes, sampling, gt_labels=None,
     L.require_cuda(anchors, assigned_gt_inds, gt_bboxes)
     n = anchors.shape[0]
     dev = anchors.device
-    labels = torch.zeros(n, dtype=torch.int32, device=dev)
-    label_w = torch.zeros(n, dtype=torch.float32, device=dev)
-    tgt = torch.zeros((n, 4), dtype=torch.float32, device=dev)
-    tgt_w = torch.zeros((n, 4), dtype=torch.float32, device=dev)
-    pos = sampling.pos_inds.long(); neg = sampling.neg_inds.long()
-    pm = pos >= 0; nm = neg >= 0
-    if pos.numel():
-        psafe = torch.where(pm, pos, torch.zeros_like(pos))
-        g = (assigned_gt_inds.long()[psafe] - 1).clamp(min=0)
-        deltas = bbox2delta(anchors[psafe].contiguous(), gt_bboxes.reshape(-1, 4)[g].contiguous(), means, stds)
-        sink = torch.where(pm, pos, torch.full_like(pos, n))           # padded slots land in a discarded row
-        ext = lambda t: torch.cat([t, t.new_zeros((1,) + tuple(t.shape[1:]))])   # noqa: E731
-        tgt = ext(tgt).index_copy(0, sink, deltas)[:n]
-        tgt_w = ext(tgt_w).index_copy(0, sink, torch.ones_like(deltas))[:n]
-        lab = torch.ones_like(pos, dtype=torch.int32) if gt_labels is None else gt_labels.to(torch.int32)[g]
-        labels = ext(labels).index_copy(0, sink, lab)[:n]
-        w = torch.full_like(pos, 1.0 if pos_weight <= 0 else float(pos_weight), dtype=torch.float32)
-        label_w = ext(label_w).index_copy(0, sink, w)[:n]
-    if neg.numel():
-        sink = torch.where(nm, neg, torch.full_like(neg, n))
-        label_w = torch.cat([label_w, label_w.new_zeros(1)]).index_copy(0, sink, torch.ones_like(neg, dtype=torch.float32))[:n]
+    labels = torch.empty(n, dtype=torch.int32, device=dev)
+    label_w = torch.empty(n, dtype=torch.float32, device=dev)
+    tgt = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    tgt_w = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    L.call("mxd_pack_targets", L.dl(anchors.float().contiguous()), L.dl(assigned_gt_inds.to(torch.int32).contiguous()),
+           L.dl(gt_bboxes.reshape(-1, 4).float().contiguous()),
+           L.dl(None if gt_labels is None else gt_labels.to(torch.int32).contiguous()),
+           L.dl(sampling.pos_inds.to(torch.int32).contiguous()), L.dl(sampling.neg_inds.to(torch.int32).contiguous()),
+           L.float4(means), L.float4(stds), float(pos_weight), L.dl(labels), L.dl(label_w), L.dl(tgt), L.dl(tgt_w),
+           L.current_stream(dev))
     return labels, label_w, tgt, tgt_w

@@ -11,15 +11,7 @@ __global__ void bbox2delta_kernel(const float4* __restrict__ p, const float4* __
                                   F4 stds, float4* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const float4 a = p[i], b = g[i];
-  const float px = __fmul_rn(__fadd_rn(a.x, a.z), 0.5f), py = __fmul_rn(__fadd_rn(a.y, a.w), 0.5f);
-  const float pw = __fadd_rn(__fsub_rn(a.z, a.x), 1.0f), ph = __fadd_rn(__fsub_rn(a.w, a.y), 1.0f);
-  const float gx = __fmul_rn(__fadd_rn(b.x, b.z), 0.5f), gy = __fmul_rn(__fadd_rn(b.y, b.w), 0.5f);
-  const float gw = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f), gh = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
-  const float dx = __fdiv_rn(__fsub_rn(gx, px), pw), dy = __fdiv_rn(__fsub_rn(gy, py), ph);
-  const float dw = log_cr(__fdiv_rn(gw, pw)), dh = log_cr(__fdiv_rn(gh, ph));
-  out[i] = make_float4(__fdiv_rn(__fsub_rn(dx, means.v[0]), stds.v[0]), __fdiv_rn(__fsub_rn(dy, means.v[1]), stds.v[1]),
-                       __fdiv_rn(__fsub_rn(dw, means.v[2]), stds.v[2]), __fdiv_rn(__fsub_rn(dh, means.v[3]), stds.v[3]));
+  out[i] = encode_box(p[i], g[i], means.v, stds.v);
 }
 
 __global__ void delta2bbox_kernel(const float4* __restrict__ r, const float4* __restrict__ d, int m, F4 means,

@@ -51,6 +51,18 @@ struct NmsSortedArgs {
 size_t nms_mask_words(int S, int n_max);
 int launch_nms_sorted(const NmsSortedArgs& a, cudaStream_t st);
 
+// Spec F encode of one (proposal, gt) pair (strict fp32, correctly rounded log).
+__device__ __forceinline__ float4 encode_box(float4 a, float4 b, const float* means, const float* stds) {
+  const float px = __fmul_rn(__fadd_rn(a.x, a.z), 0.5f), py = __fmul_rn(__fadd_rn(a.y, a.w), 0.5f);
+  const float pw = __fadd_rn(__fsub_rn(a.z, a.x), 1.0f), ph = __fadd_rn(__fsub_rn(a.w, a.y), 1.0f);
+  const float gx = __fmul_rn(__fadd_rn(b.x, b.z), 0.5f), gy = __fmul_rn(__fadd_rn(b.y, b.w), 0.5f);
+  const float gw = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f), gh = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
+  const float dx = __fdiv_rn(__fsub_rn(gx, px), pw), dy = __fdiv_rn(__fsub_rn(gy, py), ph);
+  const float dw = log_cr(__fdiv_rn(gw, pw)), dh = log_cr(__fdiv_rn(gh, ph));
+  return make_float4(__fdiv_rn(__fsub_rn(dx, means[0]), stds[0]), __fdiv_rn(__fsub_rn(dy, means[1]), stds[1]),
+                     __fdiv_rn(__fsub_rn(dw, means[2]), stds[2]), __fdiv_rn(__fsub_rn(dh, means[3]), stds[3]));
+}
+
 // Spec F decode of one box (strict fp32, correctly rounded exp).
 __device__ __forceinline__ float4 decode_box(float4 r, float4 dl, const float* means, const float* stds,
                                              float max_ratio, float hmax, float wmax, bool clip) {
