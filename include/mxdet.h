@@ -155,6 +155,19 @@ int mxd_max_iou_assign(const DLTensor* anchors, const DLTensor* gts, const DLTen
                        float pos_iou_thr, float neg_iou_thr, float min_pos_iou, float delta,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- N2  detection post-processing  (SURVEY.md 8(f) "next" row N2: mxdetection/models/bbox_heads,
+ *      /root/reference/README.md:29; BBoxHead.get_det_bboxes / multiclass_nms of mmdet 0.5).
+ *      boxes (n,4) or (n,4*C); deltas NULL (boxes are final) or (n,4) / (n,4*C) decoded per Spec F on (n,4) boxes,
+ *      clipped to (img_h,img_w) when both > 0 and divided by scale_factor; cls_score (n,C) softmaxed, column 0 =
+ *      background.  Candidates (box i, class c >= 1) with score > score_thr enter ONE class-aware NMS (ids = c-1,
+ *      at most MXD_SORT_CAP of them, best first); dets (cap,5) [x1,y1,x2,y2,score] / labels (cap) i32 (c-1), rows
+ *      past num (1) i32 are 0 / -1; cap = min(min(n*(C-1), MXD_SORT_CAP), max_per_img) (max_per_img <= 0: no cap). */
+size_t mxd_det_bboxes_workspace_bytes(long long n, int num_classes, int max_per_img);
+int mxd_det_bboxes(const DLTensor* boxes, const DLTensor* deltas, const DLTensor* cls_score, const float* means,
+                   const float* stds, int img_h, int img_w, double wh_ratio_clip, float scale_factor, float score_thr,
+                   float iou_thr, float delta, int max_per_img, DLTensor* dets, DLTensor* labels, DLTensor* num,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- N1  random sampling + target packing  (SURVEY.md 8(f) "next" row N1: mxdetection/core/anchor + core/bbox,
  *      /root/reference/README.md:16-17; RandomSampler / anchor_target_single / bbox_target_single of mmdet 0.5).
  *      RNG contract: keys (N) f32 in [0,1) are supplied by the caller; the sample is the positives (assigned > 0) /

@@ -73,7 +73,7 @@ lib.mxd_last_error.restype = c_char_p
 lib.mxd_launch_count.restype = c_uint64
 for _n in ("mxd_topk_stable_workspace_bytes", "mxd_nms_workspace_bytes", "mxd_box_nms_workspace_bytes",
            "mxd_max_iou_assign_workspace_bytes", "mxd_rpn_proposals_workspace_bytes",
-           "mxd_roi_align_workspace_bytes", "mxd_multi_proposal_workspace_bytes", "mxd_random_sample_workspace_bytes"):
+           "mxd_roi_align_workspace_bytes", "mxd_multi_proposal_workspace_bytes", "mxd_random_sample_workspace_bytes", "mxd_det_bboxes_workspace_bytes"):
     if hasattr(lib, _n):
         getattr(lib, _n).restype = c_size_t
 
@@ -173,6 +173,9 @@ _SIG = {
     "mxd_max_iou_assign_workspace_bytes": [c_int, c_int],
     "mxd_max_iou_assign": [_P, _P, _P, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P, c_size_t, _P],
     "mxd_bbox2delta": [_P, _P, _P, POINTER(c_float), POINTER(c_float), _P],
+    "mxd_det_bboxes_workspace_bytes": [ctypes.c_longlong, c_int, c_int],
+    "mxd_det_bboxes": [_P, _P, _P, POINTER(c_float), POINTER(c_float), c_int, c_int, c_double, c_float, c_float, c_float, c_float,
+                       c_int, _P, _P, _P, _P, c_size_t, _P],
     "mxd_random_sample_workspace_bytes": [ctypes.c_longlong, c_int],
     "mxd_random_sample": [_P, _P, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P],
     "mxd_pack_targets": [_P, _P, _P, _P, _P, _P, POINTER(c_float), POINTER(c_float), c_float, _P, _P, _P, _P, _P],

@@ -482,6 +482,44 @@ __global__ void boxnms_backward_kernel(const float* __restrict__ og, const int* 
   for (int c = 0; c < K; ++c) o[c] = g[c];
 }
 
+// ---- detection post-processing (BBoxHead.get_det_bboxes / multiclass_nms of mmdet 0.5) ----------
+struct DetF4 { float v[4]; };
+
+// candidate m = i * (C-1) + (c-1), c = 1..C-1: box (decoded per Spec F when deltas are given, clipped, divided by
+// the scale factor), score = cls_score[i,c], id = c-1
+__global__ void det_candidates_kernel(const float* __restrict__ boxes, int box_cols, const float* __restrict__ deltas,
+                                      int delta_cols, const float* __restrict__ score, int n, int C, DetF4 means,
+                                      DetF4 stds, float max_ratio, float hmax, float wmax, int clip, float scale,
+                                      float4* __restrict__ ob, float* __restrict__ os, int* __restrict__ oid) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= (long long)n * (C - 1)) return;
+  const int i = (int)(m / (C - 1)), c = (int)(m - (long long)i * (C - 1)) + 1;
+  const float* bp = boxes + (size_t)i * box_cols + (box_cols == 4 ? 0 : 4 * c);
+  float4 b = make_float4(bp[0], bp[1], bp[2], bp[3]);
+  if (deltas) {
+    const float* dp = deltas + (size_t)i * delta_cols + (delta_cols == 4 ? 0 : 4 * c);
+    b = decode_box(b, make_float4(dp[0], dp[1], dp[2], dp[3]), means.v, stds.v, max_ratio, hmax, wmax, clip != 0);
+    if (scale != 1.0f) b = make_float4(__fdiv_rn(b.x, scale), __fdiv_rn(b.y, scale), __fdiv_rn(b.z, scale), __fdiv_rn(b.w, scale));
+  }
+  ob[m] = b;
+  os[m] = score[(size_t)i * C + c];
+  oid[m] = c - 1;
+}
+
+__global__ void det_output_kernel(const float4* __restrict__ cb, const float* __restrict__ cs, const int* __restrict__ cid,
+                                  const int* __restrict__ keep, int cap, float* __restrict__ dets, int* __restrict__ labels) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cap) return;
+  const int m = keep[j];
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  float sc = 0.f;
+  int lab = -1;
+  if (m >= 0) { b = cb[m]; sc = cs[m]; lab = cid[m]; }
+  float* o = dets + (size_t)j * 5;
+  o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w; o[4] = sc;
+  labels[j] = lab;
+}
+
 struct NmsWs {
   int* order; float* vals; int* cnt; float4* boxes; int* ids; u64* mask; int* keep; int* keep_cnt;
   size_t bytes;
@@ -560,6 +598,94 @@ int mxd_nms(const DLTensor* boxes, const DLTensor* scores, const DLTensor* ids, 
   // keep tensor may be shorter than k: resolve writes at most keep_stride rows
   a.keep = dptr<int>(keep); a.keep_stride = cap; a.keep_cnt = dptr<int>(num_keep);
   return launch_nms_sorted(a, st);
+}
+
+struct DetWs { float4* cb; float* cs; int* cid; int* keep; void* nms; size_t bytes; };
+static DetWs det_carve(void* base, long long m, int k, int cap) {
+  DetWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (char*)base + o; };
+  w.cb = (float4*)take(sizeof(float4) * (size_t)m);
+  w.cs = (float*)take(sizeof(float) * (size_t)m);
+  w.cid = (int*)take(sizeof(int) * (size_t)m);
+  w.keep = (int*)take(sizeof(int) * (size_t)(cap > 0 ? cap : 1));
+  w.nms = take(carve(nullptr, 1, k > 0 ? k : 1).bytes);
+  w.bytes = off;
+  return w;
+}
+static inline void det_dims(long long n, int C, int max_per_img, long long* m, int* k, int* cap) {
+  *m = n * (C - 1);
+  *k = (int)std::min<long long>(*m, MXD_SORT_CAP);
+  *cap = max_per_img > 0 ? std::min(*k, max_per_img) : *k;
+}
+
+size_t mxd_det_bboxes_workspace_bytes(long long n, int num_classes, int max_per_img) {
+  long long m; int k, cap;
+  det_dims(n, num_classes, max_per_img, &m, &k, &cap);
+  return det_carve(nullptr, m, k, cap).bytes;
+}
+
+int mxd_det_bboxes(const DLTensor* boxes, const DLTensor* deltas, const DLTensor* cls_score, const float* means,
+                   const float* stds, int img_h, int img_w, double wh_ratio_clip, float scale_factor, float score_thr,
+                   float iou_thr, float delta, int max_per_img, DLTensor* dets, DLTensor* labels, DLTensor* num,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  int dev = -1, rc;
+  if ((rc = check_tensor(boxes, "boxes", F32, 2, 2, &dev))) return rc;
+  if ((rc = check_tensor(cls_score, "cls_score", F32, 2, 2, &dev))) return rc;
+  const long long n = cls_score->shape[0];
+  const int C = (int)cls_score->shape[1];
+  MXD_REQUIRE(C >= 2, MXD_EINVAL, "cls_score must be (n,C) with a background column");
+  const int bc = (int)boxes->shape[1];
+  MXD_REQUIRE(boxes->shape[0] == n && (bc == 4 || bc == 4 * C), MXD_EINVAL, "boxes must be (n,4) or (n,4*C)");
+  int dc = 0;
+  if (deltas) {
+    if ((rc = check_tensor(deltas, "deltas", F32, 2, 2, &dev))) return rc;
+    dc = (int)deltas->shape[1];
+    MXD_REQUIRE(deltas->shape[0] == n && (dc == 4 || dc == 4 * C) && bc == 4, MXD_EINVAL,
+                "deltas must be (n,4) or (n,4*C) on (n,4) boxes");
+    MXD_REQUIRE(means && stds && wh_ratio_clip > 0, MXD_EINVAL, "means/stds must be float[4], wh_ratio_clip > 0");
+  }
+  if ((rc = check_tensor(dets, "dets", F32, 2, 2, &dev))) return rc;
+  if ((rc = check_tensor(labels, "labels", I32, 1, 1, &dev))) return rc;
+  if ((rc = check_tensor(num, "num", I32, 1, 1, &dev))) return rc;
+  long long m; int k, cap;
+  det_dims(n, C, max_per_img, &m, &k, &cap);
+  MXD_REQUIRE(m < (1ll << 31), MXD_ENOTSUP, "too many candidates");
+  MXD_REQUIRE(dets->shape[0] == cap && dets->shape[1] == 5 && labels->shape[0] == cap && num->shape[0] >= 1, MXD_EINVAL,
+              "dets / labels / num must be (%d,5) / (%d) / (1)", cap, cap);
+  cudaStream_t st = as_stream(stream);
+  if (m == 0 || cap == 0) {
+    MXD_CUDA_OK(cudaMemsetAsync(dptr<int>(num), 0, sizeof(int), st));
+    return MXD_OK;
+  }
+  DetWs w = det_carve(workspace, m, k, cap);
+  MXD_REQUIRE(workspace && workspace_bytes >= w.bytes, MXD_EWORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+  MXD_REQUIRE(((uintptr_t)workspace & 255) == 0, MXD_EINVAL, "workspace must be 256-byte aligned");
+  DetF4 mu = {}, sd = {};
+  if (deltas) for (int j = 0; j < 4; ++j) { mu.v[j] = means[j]; sd.v[j] = stds[j]; }
+  const int clip = (img_h > 0 && img_w > 0) ? 1 : 0;
+  det_candidates_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(
+      dptr<float>(boxes), bc, deltas ? dptr<float>(deltas) : nullptr, dc, dptr<float>(cls_score), (int)n, C, mu, sd,
+      deltas ? (float)fabs(log(wh_ratio_clip)) : 0.0f, (float)(img_h - 1), (float)(img_w - 1), clip, scale_factor, w.cb, w.cs, w.cid);
+  MXD_POST_LAUNCH("det_candidates");
+  NmsWs nw = carve(w.nms, 1, k);
+  TopkParams p = {};
+  p.num_levels = 1; p.batch = 1;
+  p.scores[0] = w.cs; p.seg_stride[0] = m; p.elem_stride = 1;
+  p.n[0] = (int)m; p.k[0] = k; p.kmax = k;
+  p.valid_thresh = score_thr;
+  p.out_idx = nw.order; p.out_cnt = nw.cnt;
+  if ((rc = launch_topk(p, st))) return rc;
+  nms_gather_kernel<<<(k + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(w.cb), w.cid, nw.order, k, nw.boxes, nw.ids);
+  MXD_POST_LAUNCH("nms_gather");
+  NmsSortedArgs a = {};
+  a.boxes = nw.boxes; a.ids = nw.ids; a.counts = nw.cnt; a.order = nw.order;
+  a.S = 1; a.stride = k; a.n_max = k; a.thr = iou_thr; a.delta = delta; a.max_out = cap;
+  a.mask = nw.mask; a.keep = w.keep; a.keep_stride = cap; a.keep_cnt = dptr<int>(num);
+  if ((rc = launch_nms_sorted(a, st))) return rc;
+  det_output_kernel<<<(cap + 255) / 256, 256, 0, st>>>(w.cb, w.cs, w.cid, w.keep, cap, dptr<float>(dets), dptr<int>(labels));
+  MXD_POST_LAUNCH("det_output");
+  return MXD_OK;
 }
 
 size_t mxd_box_nms_workspace_bytes(int batch, int n, int topk) { return carve(nullptr, batch, eff_k(n, topk)).bytes; }
