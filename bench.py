@@ -448,14 +448,21 @@ def run_ours(args):
         secondary["cfg4a_mask_roialign_14x14_b8"] = {"rois_per_s": world * rois_m.shape[0] / (ms * 1e-3), "ms": ms,
                                                       "hbm_frac": bm / ms / 1e6 / peak_gbs, "algorithmic_bytes": bm}
         # (e) config 5 shard pipeline: assigner + proposals + RoI stage fwd/bwd (+ NCCL gather of detections at N>1)
+        side = torch.cuda.Stream(dev)     # the assigner depends on nothing the proposal / RoI chain produces:
+                                          # it runs beside the latency-bound top-k / NMS chain
+
         def pipeline_step():
-            anchor_assign(anchors, inside, gts, ngt, gl)
+            cur = torch.cuda.current_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                anchor_assign(anchors, inside, gts, ngt, gl)
             p, n = head.get_proposals(pipe_prop[0], pipe_prop[1], pipe_prop[2], pipe_prop[3], pcfg)
             fwd(); bwd()
+            cur.wait_stream(side)
             gather_detections(p, n, first_image)
         ms = timed(pipeline_step, max(it // 2, 3))
         secondary["cfg5_shard_pipeline"] = {"images_per_s": world * IMGS_PER_GPU / (ms * 1e-3), "ms": ms,
-                                            "stages": "assigner + rpn proposals + fpn roialign fwd/bwd + detection all-gather"}
+                                            "stages": "assigner (side stream) || rpn proposals + fpn roialign fwd/bwd, then detection all-gather"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
