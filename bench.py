@@ -447,6 +447,30 @@ def run_ours(args):
         bm = 2 * (map_bytes + o_m.numel() * 4)
         secondary["cfg4a_mask_roialign_14x14_b8"] = {"rois_per_s": world * rois_m.shape[0] / (ms * 1e-3), "ms": ms,
                                                       "hbm_frac": bm / ms / 1e6 / peak_gbs, "algorithmic_bytes": bm}
+        # (f) SURVEY 8(f) "next" rows at reference sizes: N1 sampling + target packing of one image's anchors, N2 detection
+        # post-processing of 1000 proposals x 81 classes
+        from mxdetection_b200.core.bbox import MaxIoUAssigner, RandomSampler, pack_targets
+        from mxdetection_b200.models.bbox_heads import get_det_bboxes
+        rng_n = np.random.default_rng(3 + first_image)
+        gts1 = gts[0, : int(a["num_gts"][0])].contiguous()
+        asg = MaxIoUAssigner(0.7, 0.3, 0.3).assign(anchors, gts1)
+        skeys = torch.rand(anchors.shape[0], device=dev, generator=gen)
+        sampler = RandomSampler(256, 0.5, -1)
+
+        def n1_step():
+            pack_targets(anchors, asg.gt_inds, gts1, sampler.sample(asg.gt_inds, skeys))
+        ms = timed(n1_step, it)
+        secondary["n1_sample256_pack_targets"] = {"ms": ms, "anchors": int(anchors.shape[0]), "images_per_s": world / (ms * 1e-3)}
+        nd, Cd = 1000, 81
+        rois_d = torch.from_numpy(np.concatenate([np.zeros((nd, 1)), syn.gt_boxes(rng_n, 800, 1344, nd)], 1).astype(np.float32)).to(dev)
+        lg = rng_n.normal(0, 2, (nd, Cd)); lg[:, 0] += 3
+        score_d = torch.from_numpy((np.exp(lg) / np.exp(lg).sum(1, keepdims=True)).astype(np.float32)).to(dev)
+        pred_d = torch.from_numpy(rng_n.normal(0, 1.0, (nd, 4 * Cd)).astype(np.float32)).to(dev)
+
+        def n2_step():
+            get_det_bboxes(rois_d, score_d, pred_d, (800, 1344), 1.0, 0.05, 0.5, 100)
+        ms = timed(n2_step, it)
+        secondary["n2_det_bboxes_1000x81"] = {"ms": ms, "images_per_s": world / (ms * 1e-3)}
         # (e) config 5 shard pipeline: assigner + proposals + RoI stage fwd/bwd (+ NCCL gather of detections at N>1)
         side = torch.cuda.Stream(dev)     # the assigner depends on nothing the proposal / RoI chain produces:
                                           # it runs beside the latency-bound top-k / NMS chain
