@@ -51,6 +51,8 @@ inline bool dtype_is(const DLTensor* t, DT d) {
 
 inline bool is_compact(const DLTensor* t) {
   if (!t->strides) return true;
+  for (int i = 0; i < t->ndim; ++i)
+    if (t->shape[i] == 0) return true;       // no element: any stride vector describes it (exporters differ)
   int64_t s = 1;
   for (int i = t->ndim - 1; i >= 0; --i) {
     if (t->shape[i] != 1 && t->strides[i] != s) return false;

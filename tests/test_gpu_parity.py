@@ -654,6 +654,57 @@ def test_mask_target_n4():
     assert got.shape == (40, 28, 28) and np.mean(got != ref) <= 1e-3        # >= 0.5 boundary pixels may flip by 1 ulp
 
 
+def test_empty_and_one_sided_inputs():
+    """No RoIs at all, an image without RoIs, no positives / no negatives to sample, no GT, no candidate above the
+    score threshold: shapes, zero fills and counts are what the reference's loops leave behind."""
+    from mxdetection_b200.ops import roi_align_fpn_forward, roi_align_fpn_backward, roi_align_backward
+    from mxdetection_b200.core.bbox import MaxIoUAssigner, RandomSampler, pack_targets
+    from mxdetection_b200.models.bbox_heads import get_det_bboxes
+    rng = np.random.default_rng(12)
+    shapes = [(2, 32, 40, 56), (2, 32, 20, 28)]
+    feats = [T(rng.normal(0, 1, s).astype(F)) for s in shapes]
+    scales = [0.25, 0.125]
+    none = T(np.zeros((0, 5), F))
+    assert tuple(roi_align_fpn_forward(feats, none, (7, 7), scales, 2).shape) == (0, 32, 7, 7)
+    g = roi_align_fpn_backward(T(np.zeros((0, 32, 7, 7), F)), none, shapes, (7, 7), scales, 2,
+                               grad_feats=[torch.full(s, 7.0, device="cuda") for s in shapes])
+    assert all(float(x.abs().max()) == 0.0 for x in g)                 # req=write: zero-filled
+    g1 = roi_align_backward(T(np.zeros((0, 32, 7, 7), F)), none, shapes[0], (7, 7), 0.25, 2)
+    assert float(g1.abs().max()) == 0.0
+    # RoIs on image 1 only: image 0's gradient planes are zeros, the output matches the oracle
+    rois = np.concatenate([np.ones((30, 1)), syn.gt_boxes(rng, 160, 224, 30)], 1).astype(F)
+    gout = rng.normal(0, 1, (30, 32, 7, 7)).astype(F)
+    out = roi_align_fpn_forward(feats, T(rois), (7, 7), scales, 2)
+    lv = oracle.map_roi_levels(rois, 2)
+    assert close(N(out), cref.roi_align_forward([N(f) for f in feats], rois, (7, 7), scales, 2, lv), 1e-5)
+    g = roi_align_fpn_backward(T(gout), T(rois), shapes, (7, 7), scales, 2)
+    gref = cref.roi_align_backward(gout, rois, shapes, (7, 7), scales, 2, lv)
+    assert all(float(x[0].abs().max()) == 0.0 for x in g) and all(close(N(x), r, 1e-4) for x, r in zip(g, gref))
+    # sampler: only negatives / only positives / nothing assigned
+    n = 5000
+    keys = T(rng.random(n).astype(F))
+    anchors = T(syn.gt_boxes(rng, 600, 800, n))
+    gts = T(syn.gt_boxes(rng, 600, 800, 3))
+    for assigned in (np.zeros(n, np.int32), np.ones(n, np.int32), np.full(n, -1, np.int32)):
+        s_ = RandomSampler(64, 0.25, -1).sample(T(assigned), keys)
+        pos, neg = oracle.targets.random_sample(assigned, N(keys), 64, 0.25, -1)
+        assert int(s_.num_pos.item()) == len(pos) and int(s_.num_neg.item()) == len(neg)
+        gp, gn = N(s_.pos_inds), N(s_.neg_inds)
+        assert np.array_equal(gp[gp >= 0], pos) and np.array_equal(gn[gn >= 0], neg)
+        lab, lw, tgt, tw = pack_targets(anchors, T(assigned), gts, s_)
+        rl, rlw, rt, rtw = oracle.targets.pack_targets(N(anchors), assigned, N(gts), pos, neg)
+        assert np.array_equal(N(lab), rl) and np.array_equal(N(lw), rlw) and np.array_equal(N(tw), rtw)
+        assert np.abs(N(tgt) - rt).max() <= 1e-6
+    # assigner without ground truth: everything negative (mmdet: assigned 0, overlaps 0)
+    a0 = MaxIoUAssigner(0.5, 0.4, 0.2).assign_batch(anchors, T(np.zeros((1, 4, 4), F)), T(np.zeros(1, np.int32)), None)
+    assert int(a0[0].abs().max()) == 0 and float(a0[1].abs().max()) == 0.0
+    # detections: every score below the threshold -> num 0, rows 0 / -1
+    rois_d = np.concatenate([np.zeros((50, 1)), syn.gt_boxes(rng, 600, 800, 50)], 1).astype(F)
+    sc = np.full((50, 5), 0.01, F); sc[:, 0] = 0.96
+    dets, labels, num = get_det_bboxes(T(rois_d), T(sc), T(rng.normal(0, 1, (50, 20)).astype(F)), (600, 800), 1.0, 0.05, 0.5, 100)
+    assert int(num.item()) == 0 and float(dets.abs().max()) == 0.0 and np.all(N(labels) == -1)
+
+
 def test_pipeline_is_cuda_graph_capturable():
     """No allocation / sync inside the library: the whole proposal stage replays from a CUDA graph."""
     from mxdetection_b200.models.rpn_heads import RPNHead, ProposalConfig
