@@ -705,6 +705,44 @@ def test_empty_and_one_sided_inputs():
     assert int(num.item()) == 0 and float(dets.abs().max()) == 0.0 and np.all(N(labels) == -1)
 
 
+def test_nms_threshold_extremes_and_identical_boxes():
+    from mxdetection_b200.ops import nms_indices
+    rng = np.random.default_rng(21)
+    n = 700
+    xy = rng.uniform(0, 400, (n, 2)); wh = rng.uniform(4, 120, (n, 2))
+    boxes = np.concatenate([xy, xy + wh], 1).astype(F)
+    scores = rng.uniform(0, 1, n).astype(F)
+    same = np.tile(boxes[:1], (n, 1))
+    for bx, thr in ((boxes, 0.0), (boxes, 1.0), (boxes, 0.999999), (same, 0.5), (same, 1.0)):
+        for delta in (0.0, 1.0):
+            ref = oracle.nms(bx, scores, thr, delta=delta)
+            keep, num = nms_indices(T(bx), T(scores), thr, delta=delta)
+            assert int(num.item()) == len(ref) and np.array_equal(N(keep)[: len(ref)], ref), (thr, delta)
+
+
+def test_roi_align_rois_outside_inverted_and_whole_image():
+    """RoIs that miss the map, inverted corners (width / height clamp to 1), RoIs larger than the map, single-pixel RoIs:
+    the planners reject what does not fit their windows and the gather path takes over - same numbers either way."""
+    from mxdetection_b200.ops import roi_align_fpn_forward, roi_align_fpn_backward
+    rng = np.random.default_rng(31)
+    shapes = [(2, 32, 48, 64), (2, 32, 24, 32), (2, 32, 12, 16)]
+    scales = [0.25, 0.125, 0.0625]
+    feats = [rng.normal(0, 1, s).astype(F) for s in shapes]
+    rois = np.array([[0, -500, -500, -300, -300], [0, 400, 300, 900, 700], [1, 100, 80, 60, 40], [1, -50, -50, 400, 300],
+                     [0, 10.3, 20.7, 10.3, 20.7], [1, 0, 0, 255, 191], [0, 250, 5, 259, 190], [1, 3, 180, 250, 195],
+                     [0, -20, 30, 15, 60], [1, 255.5, 191.5, 300, 200]], F)
+    rois = np.concatenate([rois, np.concatenate([rng.integers(0, 2, (40, 1)), syn.gt_boxes(rng, 192, 256, 40)], 1).astype(F)])
+    rois = rois[np.argsort(rois[:, 0], kind="stable")]
+    lv = oracle.map_roi_levels(rois, 3)
+    for ps in ((7, 7), (14, 14)):
+        out = roi_align_fpn_forward([T(f) for f in feats], T(rois), ps, scales, 2)
+        assert close(N(out), cref.roi_align_forward(feats, rois, ps, scales, 2, lv), 1e-5)
+        gout = rng.normal(0, 1, (rois.shape[0], 32) + ps).astype(F)
+        g = roi_align_fpn_backward(T(gout), T(rois), shapes, ps, scales, 2)
+        gref = cref.roi_align_backward(gout, rois, shapes, ps, scales, 2, lv)
+        assert all(close(N(x), r, 1e-4) for x, r in zip(g, gref))
+
+
 def test_pipeline_is_cuda_graph_capturable():
     """No allocation / sync inside the library: the whole proposal stage replays from a CUDA graph."""
     from mxdetection_b200.models.rpn_heads import RPNHead, ProposalConfig
