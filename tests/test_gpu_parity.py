@@ -564,6 +564,27 @@ def test_rpn_proposals_small_stagewise_and_end_to_end(cfgkw):
     assert np.abs(props - ro).max() <= 1e-5 * 2000 and (props == ro).mean() > 0.9999
 
 
+def test_rpn_proposals_degenerate_scores_and_tiny_maps():
+    """All scores equal (the index alone orders every level), heavy quantisation, a 32x32 image (1x1 coarse maps,
+    fewer anchors than nms_pre on every level), huge deltas (the ratio clip and the image clip decide everything)."""
+    rng = np.random.default_rng(5)
+    for (ih, iw), mode in (((160, 224), "const"), ((160, 224), "quant"), ((32, 32), "rand"), ((96, 64), "bigdelta")):
+        d = syn.rpn_inputs(7, 2, ih, iw)
+        for l in range(len(d["scores"])):
+            if mode == "const":
+                d["scores"][l][:] = 0.5
+            elif mode == "quant":
+                d["scores"][l] = (np.round(d["scores"][l] * 8) / 8).astype(F)
+            elif mode == "bigdelta":
+                d["deltas"][l] = rng.normal(0, 3.0, d["deltas"][l].shape).astype(F)
+        for cfgkw in (dict(nms_pre=300, nms_post=100, max_num=150, nms_thr=0.7), dict(nms_pre=50, nms_post=50, max_num=20, nms_thr=0.3, min_bbox_size=8)):
+            props, nv, stages = _run_rpn(d, cfgkw)
+            base = [oracle.gen_base_anchors(s, [8], [0.5, 1, 2]) for s in d["strides"]]
+            ro, rn = oracle.rpn_proposals(d["scores"], d["deltas"], base, d["feat_shapes"], d["strides"], d["img_shapes"], **cfgkw)
+            assert np.array_equal(nv, rn), (mode, cfgkw)
+            assert np.abs(props - ro).max() <= 1e-5 * 2000 and (props == ro).mean() > 0.999, (mode, cfgkw)
+
+
 def test_rpn_proposals_cfg2_full_size():
     """BASELINE config 2: 800x1088, 217 413 anchors/img, top-2000/level, NMS 0.7, post 1000, batch 2."""
     cfgkw = dict(nms_pre=2000, nms_post=1000, max_num=1000, nms_thr=0.7)
