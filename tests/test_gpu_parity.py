@@ -274,6 +274,25 @@ def test_mask_branch_cfg4_14x14():
         assert close(N(a), b, 1e-4)
 
 
+def test_host_roi_stage_images_without_rois():
+    """Images 1 and 3 of 5 carry no RoI: their gradient planes come back as zeros, the rest matches the device ops."""
+    from mxdetection_b200.ops import HostRoIStage, roi_align_fpn_forward, roi_align_fpn_backward
+    d = syn.fpn_roi_inputs(3, 5, 256, 320, 64, channels=32)
+    keep = ~np.isin(d["rois"][:, 0].astype(int), (1, 3))
+    rois, gout = d["rois"][keep], d["grad_out"][keep]
+    feats_h = [torch.from_numpy(f).pin_memory() for f in d["feats"]]
+    rois_h = torch.from_numpy(rois).pin_memory(); gout_h = torch.from_numpy(gout).pin_memory()
+    out_h = torch.full(gout.shape, 5.0).pin_memory()
+    grads_h = [torch.full(f.shape, 5.0).pin_memory() for f in d["feats"]]
+    stage = HostRoIStage([f.shape for f in d["feats"]], 64, (7, 7), d["scales"], 2, DEV, depth=2)
+    stage.forward_backward(feats_h, rois_h, gout_h, out_h, grads_h).synchronize()
+    ref = roi_align_fpn_forward([T(f) for f in d["feats"]], T(rois), (7, 7), d["scales"], 2)
+    gref = roi_align_fpn_backward(T(gout), T(rois), [f.shape for f in d["feats"]], (7, 7), d["scales"], 2)
+    assert close(out_h.numpy(), N(ref), 1e-6)
+    for a, b in zip(grads_h, gref):
+        assert close(a.numpy(), N(b), 1e-4) and float(a[1].abs().max()) == 0.0 and float(a[3].abs().max()) == 0.0
+
+
 # ================================================================ top-k (Spec B/H) ==
 # (40,40) .. (130,130): the sort's register phase alone / plus one and two shared-memory merge sizes; (8192,8192): full capacity
 @pytest.mark.parametrize("n,k", [(1, 1), (5, 10), (63, 7), (40, 40), (64, 64), (100, 100), (130, 130), (2048, 2048),
