@@ -240,6 +240,29 @@ def test_fpn_roi_stage_cfg3_shard_full_size(roi_path):
         assert close(N(a), b, 1e-4)
 
 
+def test_roi_align_crowded_band_and_tile():
+    """1200 RoIs in one corner of one image (600 of them identical): one band / one tile carries far more RoIs than a
+    shared-memory table chunk or a message batch holds; the identical RoIs make the backward accumulate 600 times
+    into the same pixels (order-dependent rounding: 1e-4 relative still holds)."""
+    from mxdetection_b200.ops import roi_align_fpn_forward, roi_align_fpn_backward
+    rng = np.random.default_rng(51)
+    shapes = [(2, 32, 64, 80), (2, 32, 32, 40), (2, 32, 16, 20), (2, 32, 8, 10)]
+    scales = [0.25, 0.125, 0.0625, 0.03125]
+    feats = [rng.normal(0, 1, s).astype(F) for s in shapes]
+    xy = rng.uniform(0, 60, (600, 2)); wh = rng.uniform(8, 40, (600, 2))
+    crowd = np.concatenate([np.zeros((600, 1)), xy, xy + wh], 1)
+    same = np.tile(np.array([[0, 12.5, 9.25, 47.0, 39.5]]), (600, 1))
+    rois = np.concatenate([crowd, same, np.array([[1, 100, 100, 180, 170]])]).astype(F)
+    lv = oracle.map_roi_levels(rois, 4)
+    out = roi_align_fpn_forward([T(f) for f in feats], T(rois), (7, 7), scales, 2)
+    assert close(N(out), cref.roi_align_forward(feats, rois, (7, 7), scales, 2, lv), 1e-5)
+    gout = rng.normal(0, 1, (rois.shape[0], 32, 7, 7)).astype(F)
+    g = roi_align_fpn_backward(T(gout), T(rois), shapes, (7, 7), scales, 2)
+    gref = cref.roi_align_backward(gout, rois, shapes, (7, 7), scales, 2, lv)
+    for x, r in zip(g, gref):
+        assert np.all(np.abs(N(x) - r) <= 1e-4 * np.maximum(1.0, np.abs(r)) + 1e-4 * np.abs(r).max() * 0.01)
+
+
 def test_host_roi_stage_pipeline_matches_device_path():
     """Host-buffer entry (H2D | fwd+bwd | D2H pipelined per image over three streams) == the plain device ops."""
     from mxdetection_b200.ops import HostRoIStage, roi_align_fpn_forward, roi_align_fpn_backward
