@@ -92,3 +92,24 @@ def test_host_anchor_tables_match_oracle():
             assert np.array_equal(AnchorGenerator(base, scales, ratios, sm).base_anchors,
                                   oracle.gen_base_anchors(base, scales, ratios, sm))
     assert np.array_equal(generate_anchors_mx(), oracle.generate_anchors_mx())
+
+
+def test_new_workspace_queries_and_config_cache():
+    """Workspace sizes of the N1 / N2 entry points cover their buffers, and RPNHead builds its config struct once per
+    level geometry (host logic only: nothing is launched)."""
+    from mxdetection_b200 import _lib as L
+    from mxdetection_b200.models.rpn_heads import RPNHead, ProposalConfig
+    n = 268569
+    assert L.lib.mxd_random_sample_workspace_bytes(n, 256) >= 2 * n * 4 + 2 * 256 * 4
+    m = 1000 * 80
+    assert L.lib.mxd_det_bboxes_workspace_bytes(1000, 81, 100) >= m * (16 + 4 + 4) + L.lib.mxd_nms_workspace_bytes(m, L.MXD_SORT_CAP)
+    # W x (W+1) x 64 mask words for k boxes (band-major layout with the transposed-diagonal slot)
+    W = (2000 + 63) // 64
+    assert L.lib.mxd_nms_workspace_bytes(2000, -1) >= W * (W + 1) * 64 * 8
+    head = RPNHead()
+    sizes = [(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)]
+    a = head._config(sizes, ProposalConfig(nms_pre=300))
+    assert head._config([tuple(s) for s in sizes], ProposalConfig(nms_pre=300)) is a
+    assert head._config(sizes, ProposalConfig(nms_pre=301)) is not a
+    assert head._config(sizes[:4] + [(3, 5)], ProposalConfig(nms_pre=300)) is not a
+    assert a.num_levels == 5 and a.nms_pre == 300 and a.feat_w[1] == 28
