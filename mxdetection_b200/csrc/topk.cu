@@ -25,7 +25,7 @@ namespace cg = cooperative_groups;
 namespace mxd {
 
 constexpr int kTopkThreads = 1024;
-constexpr int kTopkCluster = 8;
+constexpr int kTopkCluster = 8;               // largest cluster; launches with many segments use 4 (see launch_topk)
 constexpr int kCap = MXD_SORT_CAP;
 constexpr int kRadixBits = 11;
 constexpr int kRadixBins = 1 << kRadixBits;
@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __g
   __shared__ int s_cnts[kTopkCluster];
 
   const int rank = CLUSTER ? (int)cg::this_cluster().block_rank() : 0;
-  const int s = CLUSTER ? blockIdx.x / kTopkCluster : blockIdx.x;
+  const int csz = CLUSTER ? (int)cg::this_cluster().num_blocks() : 1;     // 8 or 4 CTAs
+  const int s = CLUSTER ? blockIdx.x / csz : blockIdx.x;
   const int b = s / p.num_levels, l = s - b * p.num_levels;
   const int n = p.n[l], k = p.k[l];
   const int es = p.elem_stride;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __g
   if (CLUSTER && n > kCap) {
     cg::cluster_group cluster = cg::this_cluster();
     const int G = (k <= 2048) ? 4096 : kCap;
-    const int gpc = G / kTopkCluster;            // groups owned by this CTA (512 or 1024)
+    const int gpc = G / csz;                     // groups owned by this CTA (512 or 1024)
     const int rows = kTopkThreads / gpc;         // threads per group (2 or 1)
     const int gl = tid % gpc, tr = tid / gpc;
     const int nt = (n + G - 1) / G;              // elements of a group: i = t*G + rank*gpc + gl, t < nt
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __g
     __syncthreads();
     if (tr == 0) {
       for (int r = 1; r < rows; ++r) { const u64 o = funnel[r * gpc + gl]; m = o > m ? o : m; }
-      for (int dst = 0; dst < kTopkCluster; ++dst)       // all-gather: every CTA gets all G maxima
+      for (int dst = 0; dst < csz; ++dst)                // all-gather: every CTA gets all G maxima
         cluster.map_shared_rank(keys, dst)[rank * gpc + gl] = m;
     }
     cluster.sync();
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __g
     int off = 0, total = 0;
     {
       const int* c0 = cluster.map_shared_rank(s_cnts, 0);
-      for (int q = 0; q < kTopkCluster; ++q) {
+      for (int q = 0; q < csz; ++q) {
         const int cq = c0[q];
         if (q < rank) off += cq;
         total += cq;
@@ -482,12 +483,20 @@ int launch_topk(const TopkParams& p, cudaStream_t st) {
     MXD_CUDA_OK(cudaFuncSetAttribute(topk_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * smem));
   }
   if (big && (long long)S * kTopkCluster < (1ll << 31)) {
+    // 8 CTAs per segment while all clusters are co-resident (one CTA per SM); with more segments than that a
+    // second wave of clusters costs more than the longer per-CTA scans of 4-CTA clusters.  G = 8192 group maxima
+    // (k > 2048) need 1024 groups per CTA: 8 CTAs.
+    int kbig = 0;
+    for (int l = 0; l < p.num_levels; ++l) kbig = std::max(kbig, p.k[l]);
+    int sms = 148;
+    { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int csz = (S * kTopkCluster > sms && kbig <= 2048) ? 4 : kTopkCluster;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(S * kTopkCluster)); cfg.blockDim = dim3(kTopkThreads);
+    cfg.gridDim = dim3((unsigned)(S * csz)); cfg.blockDim = dim3(kTopkThreads);
     cfg.dynamicSmemBytes = 2 * smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = kTopkCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     MXD_CUDA_OK(cudaLaunchKernelEx(&cfg, topk_segment_kernel<true>, p));
   } else {
