@@ -63,7 +63,7 @@ class RpnConfig(Structure):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            "libmxdet_sm100.so is not built (expected at %s). Run `python -m mxdetection_b200.build` "
+            "libmxdet_sm100.so is not built (expected at %s). Run `python mxdetection_b200/build.py` "
             "(needs nvcc with sm_100a support). There is no CPU fallback." % LIB_PATH)
     return ctypes.CDLL(LIB_PATH)
 

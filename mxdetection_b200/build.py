@@ -1,6 +1,6 @@
 """Builds libmxdet_sm100.so in-tree with nvcc for sm_100a (no JIT cache).
 
-`python -m mxdetection_b200.build` or `build_library()`; the resulting .so is
+`python mxdetection_b200/build.py` (by path: importing the package needs the built library) or `build_library()`; the resulting .so is
 git-ignored but travels to the GPU box with the gpurun snapshot.
 """
 import hashlib

@@ -11,8 +11,12 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with `-m gpu` through gpurun")
     # the product library and the C oracle are build artefacts; make sure they exist before collection
-    from mxdetection_b200.build import build_library
-    build_library()
+    # build.py is loaded by path: importing the package itself needs the built library (no CPU fallback)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_mxd_build", os.path.join(ROOT, "mxdetection_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build_library()
     from oracle import cref
     cref.build()
 
