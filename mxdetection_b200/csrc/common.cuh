@@ -132,11 +132,13 @@ __device__ __forceinline__ bool box_iou_gt(const float4& a, float area_a, const 
   if (!(iw > 0.0f) || !(ih > 0.0f)) return false;
   const float inter = __fmul_rn(iw, ih);
   const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
-  if (thr > 0.0f && uni > 0.0f && uni < 3.0e38f) {
-    const float p = __fmul_rn(thr, uni);
-    if (inter > __fmul_rn(p, 1.00000036f)) return true;
-    if (inter < __fmul_rn(p, 0.99999964f)) return false;
-  }
+  // straight-line form of: if (guard) { if (inter > p*(1+e)) return true; if (inter < p*(1-e)) return false; }
+  // - same products, same comparisons, one rarely taken branch instead of three
+  const float p = __fmul_rn(thr, uni);
+  const bool yes = inter > __fmul_rn(p, 1.00000036f);
+  const bool no = inter < __fmul_rn(p, 0.99999964f);
+  const bool guard = thr > 0.0f && uni > 0.0f && uni < 3.0e38f;
+  if (guard && (yes || no)) return yes;
   return __fdiv_rn(inter, uni) > thr;
 }
 
