@@ -269,3 +269,41 @@ def test_next_row_oracles_hand_cases():
     m = np.stack([np.ones((20, 30), np.uint8), np.zeros((20, 30), np.uint8)])
     mt = t.mask_target(np.array([[2, 2, 25, 17], [2, 2, 25, 17]], np.float32), [0, 1], m, 14)
     assert mt[0].all() and not mt[1].any()
+
+
+# ------------------------------------------------ size-independent properties of the oracle ----
+def test_oracle_properties_adjoint_linearity_idempotence():
+    """The properties the GPU tests lean on at full size, checked on the oracle itself: RoIAlign backward is the
+    adjoint of forward (<fwd(x), g> == <x, bwd(g)>), forward is linear in the features, NMS of its own survivors
+    keeps all of them, stable top-k equals a lexsort, the sampler honours its quotas."""
+    rng = np.random.default_rng(123)
+    data = rng.normal(0, 1, (2, 3, 20, 28)).astype(F)
+    data2 = rng.normal(0, 1, data.shape).astype(F)
+    rois = np.array([[0, 3.2, 4.1, 60.7, 50.3], [1, -5, -3, 30, 40], [1, 90, 60, 111, 79], [0, 10, 10, 10, 10]], F)
+    g = rng.normal(0, 1, (4, 3, 7, 7)).astype(F)
+    for sr in (2, -1):
+        out = oracle.roi_align_forward(data, rois, (7, 7), 0.25, sr).astype(np.float64)
+        gin = oracle.roi_align_backward(g, rois, data.shape, (7, 7), 0.25, sr).astype(np.float64)
+        lhs, rhs = (out * g).sum(), (data.astype(np.float64) * gin).sum()
+        assert abs(lhs - rhs) <= 1e-3 * max(1.0, abs(lhs))
+        both = oracle.roi_align_forward(data + data2, rois, (7, 7), 0.25, sr)
+        sep = oracle.roi_align_forward(data, rois, (7, 7), 0.25, sr) + oracle.roi_align_forward(data2, rois, (7, 7), 0.25, sr)
+        assert np.abs(both - sep).max() <= 1e-5
+    n = 400
+    xy = rng.uniform(0, 200, (n, 2)); wh = rng.uniform(4, 80, (n, 2))
+    boxes = np.concatenate([xy, xy + wh], 1).astype(F)
+    scores = rng.uniform(0, 1, n).astype(F)
+    keep = oracle.nms(boxes, scores, 0.5, delta=1.0)
+    assert np.array_equal(oracle.nms(boxes[keep], scores[keep], 0.5, delta=1.0), np.arange(len(keep)))
+    s = (np.round(rng.uniform(0, 1, 5000) * 50) / 50).astype(F)
+    assert np.array_equal(oracle.topk_stable(s, 300), np.lexsort((np.arange(s.size), -s.astype(np.float64)))[:300])
+    assigned = rng.integers(-1, 4, 3000).astype(np.int32)
+    keys = rng.random(3000).astype(F)
+    for num, frac, ub in ((256, 0.5, -1), (64, 0.25, 2), (4000, 0.5, -1)):
+        pos, neg = oracle.targets.random_sample(assigned, keys, num, frac, ub)
+        assert len(pos) <= int(num * frac) and len(pos) + len(neg) <= num
+        assert np.all(assigned[pos] > 0) and np.all(assigned[neg] == 0) and len(set(pos)) == len(pos)
+        if ub >= 0:
+            assert len(neg) <= ub * max(1, len(pos))
+        if len(pos) < (assigned > 0).sum():            # the sample is the largest keys among the positives
+            assert keys[pos].min() >= np.sort(keys[assigned > 0])[-len(pos)] - 0
