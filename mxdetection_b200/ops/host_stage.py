@@ -52,6 +52,8 @@ class HostRoIStage:
                       for _ in range(self.depth)]
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
         self.max_rois = R
+        # image-local copy of the RoI table (batch index 0): pinned once, cudaHostAlloc per step would serialise the streams
+        self._rois0 = torch.empty((self.shapes[0][0] * R, 5), dtype=torch.float32).pin_memory()
 
     def forward_backward(self, feats_h, rois_h, grad_out_h, out_h, grads_h):
         """Enqueues the whole step and returns an event; ``event.synchronize()`` (or ``torch.cuda.synchronize()``)
@@ -64,7 +66,10 @@ class HostRoIStage:
         if counts.max(initial=0) > self.max_rois:
             raise ValueError("HostRoIStage: %d RoIs on one image, capacity %d" % (counts.max(), self.max_rois))
         starts = np.concatenate([[0], np.cumsum(counts)])
-        rois0 = rois_h.clone().pin_memory()
+        if getattr(self, "_last_in", None) is not None:
+            self._last_in.synchronize()                  # the previous step's H2D copies have read the pinned table
+        rois0 = self._rois0[: rois_h.shape[0]]
+        rois0.copy_(rois_h)
         rois0[:, 0] = 0                                  # every slot holds one image
         bins = self.pooled[0] * self.pooled[1]
         C, Cs = self.C, self.Cs
@@ -111,6 +116,7 @@ class HostRoIStage:
                     for l, g in enumerate(grads_h):
                         g[i:i + 1, c0:c0 + Cs].copy_(sl["grads"][l], non_blocking=True)
                     ev_out[k] = torch.cuda.Event(); ev_out[k].record(self.s_out)
+        self._last_in = torch.cuda.Event(); self._last_in.record(self.s_in)
         for s in (self.s_in, self.s_cmp, self.s_out):
             cur.wait_stream(s)
         done = torch.cuda.Event(); done.record(cur)
