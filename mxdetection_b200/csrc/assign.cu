@@ -3,13 +3,13 @@
 // (/root/reference/README.md:16-17); bbox_overlaps / bbox_assign_wrt_overlaps of
 // mmdet 0.5, mx.nd.contrib.box_iou of mxnet 1.3.0.
 //
-// The G x N overlap matrix is never materialised.  Pass 1: one thread per
-// anchor walks the GTs held in shared memory, tracks max / first argmax, and
-// the per-GT maximum is reduced warp-wide with one REDUX on the orderable
-// uint image of the (non-negative) IoU, then CTA-wide in shared memory, then
-// with one global atomicMax per (CTA, GT).  Pass 2 re-evaluates the same fp32
-// expression (bit-identical) to apply the `overlaps[g,n] == gt_max[g]`
-// low-quality rule; the last (largest) g wins, as the ascending loop of Spec E.
+// The G x N overlap matrix is never materialised.  Pass 1: every thread carries four anchors and walks the GTs held
+// in shared memory - but only the GTs whose grown window meets the warp's bounding box (32 windows per ballot);
+// it tracks max / first argmax, and the per-GT maximum is reduced warp-wide with one REDUX on the orderable uint
+// image of the (non-negative) IoU, then CTA-wide in shared memory, then with one global atomicMax per (CTA, GT).
+// Pass 2 re-evaluates the same fp32 expression (bit-identical) to apply the `overlaps[g,n] == gt_max[g]`
+// low-quality rule - only for GTs whose maximum does not exceed the anchor's own; the last (largest) g wins, as the
+// ascending loop of Spec E.
 #include "common.cuh"
 
 namespace mxd {
