@@ -13,8 +13,9 @@
 //                       (3) if more than CAP keys pass (adversarial input) an exact
 //                           11-bit radix select narrows them to exactly k first.
 //
-// Segments longer than CAP (the 160 k-anchor FPN level) run on a thread-block CLUSTER of 8 CTAs: CTA r owns
-// the groups [r*G/8, (r+1)*G/8) and therefore a strided 1/8 of the scores, the group maxima are all-gathered
+// Segments longer than CAP (the 160 k-anchor FPN level) run on a thread-block CLUSTER of 8 CTAs (4 when the launch
+// carries more segments than 8-CTA clusters can be co-resident): CTA r owns the groups [r*G/8, (r+1)*G/8) and
+// therefore a strided 1/8 of the scores, the group maxima are all-gathered
 // through distributed shared memory, every CTA derives the same bound L, compacts its own share, and the
 // survivors are funnelled into CTA 0 for the final sort (one CTA scanning 650 KB twice measured 138 us).
 #include <cooperative_groups.h>
