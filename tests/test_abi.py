@@ -113,3 +113,18 @@ def test_new_workspace_queries_and_config_cache():
     assert head._config(sizes, ProposalConfig(nms_pre=301)) is not a
     assert head._config(sizes[:4] + [(3, 5)], ProposalConfig(nms_pre=300)) is not a
     assert a.num_levels == 5 and a.nms_pre == 300 and a.feat_w[1] == 28
+
+
+def test_every_operator_section_of_the_header_cites_the_reference():
+    """include/mxdet.h: each operator section names the reference interface it replaces (file:line)."""
+    import re
+    h = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "mxdet.h")).read()
+    secs = re.split(r"(?=/\* ---- )", h)[1:]
+    assert len(secs) >= 9
+    for s in secs:
+        title = s.split("\n", 1)[0]
+        if "library" in title:                    # version / error string / launch counter: no reference counterpart
+            continue
+        head = s.split("*/", 1)[0]
+        assert re.search(r"/root/reference/README\.md:\d+", head), title
+        assert re.findall(r"\b(mxd_\w+)\s*\(", s), title
