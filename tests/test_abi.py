@@ -128,3 +128,29 @@ def test_every_operator_section_of_the_header_cites_the_reference():
         head = s.split("*/", 1)[0]
         assert re.search(r"/root/reference/README\.md:\d+", head), title
         assert re.findall(r"\b(mxd_\w+)\s*\(", s), title
+
+
+def test_product_package_never_imports_the_oracle_and_has_no_cpu_path():
+    """The oracle is test infrastructure: nothing under mxdetection_b200/ may import or execute it, and no product
+    module may compute on the CPU behind the caller's back (torch CPU ops on tensor data, numpy kernels)."""
+    import ast
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mxdetection_b200")
+    offenders = []
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            path = os.path.join(dp, f)
+            tree = ast.parse(open(path).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                    offenders.append(path)
+    assert not offenders, offenders
+    # the C sources reference the oracle nowhere either
+    for f in os.listdir(os.path.join(root, "csrc")):
+        assert "oracle" not in open(os.path.join(root, "csrc", f)).read().lower(), f
