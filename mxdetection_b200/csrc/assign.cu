@@ -140,9 +140,14 @@ __global__ void __launch_bounds__(kAssignThreads) assign_pass1_kernel(AssignArgs
           float iou = 0.0f;
           if (hit || !(__fadd_rn(ga, area[q]) > 0.0f)) iou = iou_spec_d(me[q], area[q], g, ga, a.delta);
           if (iou > best[q]) { best[q] = iou; arg[q] = g0 + i; }   // strict > keeps the lowest g on ties
-          any_hit = any_hit || hit;
-          // NaN / negative IoU (degenerate boxes) never feed gt_max: see DESIGN.md
+          // Spec D/E: 0/0 = NaN propagates through both maxima as in numpy / torch (max_ov = NaN at the first NaN g, so
+          // the row stays -1; gt_max = NaN, so the low-quality rule skips that GT).  0x7fc00000 orders above +inf as uint.
+          const bool isnan_ = iou != iou;
+          if (isnan_ && best[q] == best[q]) { best[q] = iou; arg[q] = g0 + i; }
+          any_hit = any_hit || hit || isnan_;
+          // IoU is in [+0, 1] or -0 or NaN (a hit needs two boxes of positive width and height): uint order = float order
           if (iou > 0.0f) bits = max(bits, __float_as_uint(iou));
+          if (isnan_) bits = 0x7fc00000u;
         }
         if (__any_sync(0xffffffffu, any_hit)) {
           const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);

@@ -8,12 +8,14 @@
 // Four launches for the whole batch, no host round trip (the reference style is a
 // Python loop over images x levels with a D2H mask reduce):
 //   topk_segment (+decode)  ->  nms_mask  ->  nms_resolve  ->  rpn_collect
+#include <algorithm>
 #include "internal.h"
 
 namespace mxd {
 
 typedef unsigned long long u64;
 constexpr int kCollectThreads = 1024;
+constexpr int kCollectCap = 56 * 1024;     // concatenated kept scores held in shared memory (224 KB of the 227 KB)
 
 struct CollectArgs {
   const float4* boxes;   // (S,kmax)
@@ -32,7 +34,7 @@ struct CollectArgs {
 // out[rank]; bit-identical to a stable sort of the concatenation.
 __global__ void __launch_bounds__(kCollectThreads, 1) rpn_collect_kernel(CollectArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sc = reinterpret_cast<float*>(smem_raw);     // concatenated kept scores (<= MXD_SORT_CAP)
+  float* sc = reinterpret_cast<float*>(smem_raw);     // concatenated kept scores (<= kCollectCap)
   __shared__ int s_off[MXD_MAX_LEVELS + 1];
   // grid (B, parts): every CTA loads the image's kept scores (the binary searches need all lists) and ranks
   // a 1/parts share of the candidates - the ranking is a chain of dependent shared-memory reads
@@ -118,8 +120,10 @@ static int rpn_dims(const mxd_rpn_config* c, int* kmax, int* keep_stride) {
   }
   if (km < 1) km = 1;
   const int ks = (c->nms_post > 0 && c->nms_post < km) ? c->nms_post : km;
-  MXD_REQUIRE((long long)ks * c->num_levels <= MXD_SORT_CAP, MXD_ENOTSUP,
-              "num_levels*nms_post = %lld exceeds %d", (long long)ks * c->num_levels, MXD_SORT_CAP);
+  // the per-image merge ranks every kept candidate against the other levels' lists in shared memory; the stock
+  // training config of the lineage (nms_pre = nms_post = max_num = 2000 on 5 levels = 10 000 candidates) fits
+  MXD_REQUIRE((long long)ks * c->num_levels <= kCollectCap, MXD_ENOTSUP,
+              "num_levels*nms_post = %lld exceeds %d", (long long)ks * c->num_levels, kCollectCap);
   *kmax = km;
   *keep_stride = ks;
   return MXD_OK;
@@ -225,10 +229,11 @@ int mxd_rpn_proposals(const DLTensor* const* scores, const DLTensor* const* delt
   c.boxes = w.boxes; c.vals = w.vals; c.keep = w.keep; c.keep_cnt = w.keep_cnt;
   c.L = L; c.kmax = km; c.keep_stride = ks; c.max_num = cfg->max_num;
   c.out = dptr<float>(proposals); c.num_valid = dptr<int>(num_valid);
-  const int smem = MXD_SORT_CAP * (int)sizeof(float);
+  const int smem = std::max(L * ks, 1) * (int)sizeof(float);
   static unsigned long long seen = 0;
   if (first_use_on_device(&seen))
-    MXD_CUDA_OK(cudaFuncSetAttribute(rpn_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MXD_CUDA_OK(cudaFuncSetAttribute(rpn_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kCollectCap * (int)sizeof(float)));
   rpn_collect_kernel<<<dim3(B, 4), kCollectThreads, smem, st>>>(c);
   MXD_POST_LAUNCH("rpn_collect");
   return MXD_OK;

@@ -227,7 +227,8 @@ void ora_max_iou_assign(const float* anchors, int N, const float* gts, int G, co
     for (int g = 0; g < G; ++g) {
       const float v = iou_d(anchors + (size_t)n * 4, gts + (size_t)g * 4, delta);
       if (v > best) { best = v; arg = g; }
-      if (v > gt_max[g]) gt_max[g] = v;
+      if (v != v && best == best) { best = v; arg = g; }          /* NaN propagates (numpy / torch max), first NaN g */
+      if (v > gt_max[g] || v != v) gt_max[g] = v;                 /* ... and through the per-GT maximum */
     }
     max_ov[n] = best;
     if (best >= 0.0f && best < neg) assigned[n] = 0;

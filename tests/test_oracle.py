@@ -158,6 +158,22 @@ def test_assign_c_vs_numpy_random():
     assert (a[0] > 0).sum() >= 1
 
 
+def test_assign_nan_propagates_like_numpy_max():
+    """Spec D: 0/0 = NaN is not special-cased.  It propagates through the per-anchor and the per-GT maximum
+    (numpy / torch max semantics): the anchor row stays -1, the GT takes no part in the low-quality rule."""
+    gts = np.array([[50, 60, 50, 80], [10, 10, 40, 40], [100, 100, 130, 130]], F)      # GT0: zero area at delta 0
+    anchors = np.array([[10, 10, 10, 10],      # zero-area anchor: 0/0 with GT0 only
+                        [10, 10, 40, 40],      # == GT1
+                        [100, 100, 130, 120],  # IoU 2/3 with GT2: its best
+                        [300, 300, 320, 320]], F)
+    a, m, _ = oracle.max_iou_assign(anchors, gts, None, 0.7, 0.3, 0.3, delta=0.0)
+    assert np.isnan(m[0]) and a[0] == -1 and a[1] == 2 and a[2] == 3 and a[3] == 0
+    c = cref.max_iou_assign_batch(anchors, gts[None], None, None, None, 0.7, 0.3, 0.3, 0.0)
+    assert np.array_equal(c[0][0], a) and np.array_equal(c[1][0], m, equal_nan=True)
+    # a NaN in GT0's row (from anchor 0) makes gt_max[0] NaN: no low-quality assignment to GT0 anywhere
+    assert not (a == 1).any()
+
+
 # ------------------------------------------------------------ Specs F, G ----------
 def test_codec_roundtrip_and_clip():
     rng = np.random.default_rng(3)
