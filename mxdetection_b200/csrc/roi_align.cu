@@ -9,6 +9,7 @@
 // tables (index, weights, validity) are computed once per CTA in shared
 // memory - they are shared by every channel - then each thread produces
 // outputs (c, ph, pw) with coalesced stores and read-only-path tap loads.
+#include <algorithm>
 #include "roi_align.cuh"
 
 namespace mxd {
@@ -173,7 +174,8 @@ size_t mxd_roi_align_workspace_bytes(int num_rois, int batch, int channels, int 
   if (num_levels < 1 || num_levels > MXD_MAX_LEVELS || !feat_h || !feat_w) return 0;
   const size_t a = plane_workspace_bytes(num_rois, batch, num_levels, feat_h, feat_w, channels, pooled_h, pooled_w, sample_ratio);
   const size_t b = tile_bwd_workspace_bytes(num_rois, batch, num_levels, feat_h, feat_w, channels, pooled_h, pooled_w, sample_ratio);
-  return a > b ? a : b;
+  const size_t r = ring_workspace_bytes(num_rois, batch, num_levels, feat_h, feat_w, channels, pooled_h, pooled_w, sample_ratio);
+  return std::max(a, std::max(b, r));
 }
 
 int mxd_roi_align_fpn_forward(const DLTensor* const* feats, int num_levels, const float* spatial_scales,
@@ -186,6 +188,9 @@ int mxd_roi_align_fpn_forward(const DLTensor* const* feats, int num_levels, cons
   const int* lv = levels ? dptr<int>(levels) : nullptr;
   if (workspace) {
     int handled = 0;
+    if ((rc = ring_forward(d, dptr<float>(rois), lv, dptr<float>(out), R, pooled_h, pooled_w, sample_ratio,
+                           finest_scale, workspace, workspace_bytes, as_stream(stream), &handled))) return rc;
+    if (handled) return MXD_OK;
     if ((rc = plane_forward(d, dptr<float>(rois), lv, dptr<float>(out), R, pooled_h, pooled_w, sample_ratio,
                             finest_scale, workspace, workspace_bytes, as_stream(stream), &handled))) return rc;
     if (handled) return MXD_OK;

@@ -132,6 +132,11 @@ int plane_backward(const FpnDesc& d, const float* rois, const int* levels, const
                    int PW, int sr, float finest, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st,
                    int* handled);
 
+// ---- row-ring forward (roi_align_ring.cu): same convention -------------------------
+size_t ring_workspace_bytes(int R, int N, int L, const int* Hs, const int* Ws, int C, int PH, int PW, int sr);
+int ring_forward(const FpnDesc& d, const float* rois, const int* levels, float* out, int R, int PH, int PW, int sr,
+                 float finest, void* ws, size_t ws_bytes, cudaStream_t st, int* handled);
+
 // ---- tile-resident backward (roi_align_tile_bwd.cu): same convention --------------
 size_t tile_bwd_workspace_bytes(int R, int N, int L, const int* Hs, const int* Ws, int C, int PH, int PW, int sr);
 int tile_backward(const FpnDesc& d, const float* rois, const int* levels, const float* gout, int R, int PH,

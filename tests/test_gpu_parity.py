@@ -47,7 +47,7 @@ def _native_library_is_the_one_running():
 
 # =============================================================== RoIAlign (Spec A) ==
 @pytest.mark.parametrize("name", ["roi_align_a", "roi_align_b", "roi_align_c"])
-def test_roi_align_golden(golden_dir, name):
+def test_roi_align_golden(golden_dir, name, roi_path):
     from mxdetection_b200.ops import roi_align_forward, roi_align_backward
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     ps = tuple(int(v) for v in g["pooled"]); sc = float(g["scale"]); sr = int(g["sample_ratio"])
@@ -57,13 +57,20 @@ def test_roi_align_golden(golden_dir, name):
     assert close(gin, g["grad_in"], 1e-4)
 
 
-@pytest.fixture(params=["plane", "gather"])
+@pytest.fixture(params=["ring", "plane", "gather"])
 def roi_path(request):
-    """Both RoIAlign code paths of the library: plane-resident (workspace given) and gather (workspace NULL)."""
+    """The RoIAlign code paths of the library: row-ring forward (forced even for tiny inputs) + tile backward, band
+    (plane-resident) forward + tile backward, and gather (workspace NULL)."""
     import mxdetection_b200.ops.roi_align as ra
     old = ra.USE_PLANE_KERNELS
-    ra.USE_PLANE_KERNELS = request.param == "plane"
+    ra.USE_PLANE_KERNELS = request.param != "gather"
+    os.environ.pop("MXD_NO_RING", None); os.environ.pop("MXD_RING_FORCE", None)
+    if request.param == "ring":
+        os.environ["MXD_RING_FORCE"] = "1"
+    elif request.param == "plane":
+        os.environ["MXD_NO_RING"] = "1"
     yield request.param
+    os.environ.pop("MXD_NO_RING", None); os.environ.pop("MXD_RING_FORCE", None)
     ra.USE_PLANE_KERNELS = old
 
 
@@ -122,7 +129,7 @@ def test_roi_align_tile_backward_paths(C, H, W, R, PS):
 
 
 @pytest.mark.parametrize("seed", range(24))
-def test_roi_align_fpn_fuzz_shapes(seed):
+def test_roi_align_fpn_fuzz_shapes(seed, roi_path):
     """Random FPN geometries through the shipped fast paths (stream forward / tile backward) and their fallbacks:
     odd and 4-aligned widths, 1-4 levels, 32-96 channels, 7x7 and 14x14, RoIs of every size incl. out of image."""
     from mxdetection_b200.ops import roi_align_fpn_forward, roi_align_fpn_backward
@@ -263,7 +270,24 @@ def test_fpn_roi_stage_cfg3_benchmarked_shape_all_8_images():
         assert close(N(a), 2 * b, 1e-4)
 
 
-def test_roi_align_crowded_band_and_tile():
+@pytest.mark.parametrize("W,C", [(400, 20), (512, 8), (520, 8), (352, 6), (356, 4)])
+def test_roi_align_ring_wide_maps_and_class_edges(W, C, roi_path):
+    """Row pitch classes of the ring forward: 352 / 704 / 1408 / 2048 bytes.  W = 352 is the widest 2-channel class,
+    356..512 run one channel per unit, 520 exceeds every class (the band kernels take the call); tall maps wrap the ring."""
+    from mxdetection_b200.ops import roi_align_forward
+    rng = np.random.default_rng(W + C)
+    H = 150
+    data = rng.standard_normal((2, C, H, W)).astype(F)
+    R = 120
+    x1 = rng.uniform(-10, W * 4 - 20, R); y1 = rng.uniform(-10, H * 4 - 20, R)
+    bw = np.exp(rng.uniform(np.log(8), np.log(300), R)); bh = np.exp(rng.uniform(np.log(8), np.log(500), R))
+    rois = np.stack([rng.integers(0, 2, R), x1, y1, x1 + bw, y1 + bh], 1).astype(F)
+    rois[:4] = [[0, 0, 0, W * 4 - 1, 40], [1, W * 4 - 60, H * 4 - 60, W * 4 + 5, H * 4 + 5], [0, 3, 500, 200, 599.5], [1, 0, 0, 30, H * 4 - 1]]
+    out = N(roi_align_forward(T(data), T(rois), (7, 7), 0.25, 2))
+    assert close(out, cref.roi_align_forward(data, rois, (7, 7), 0.25, 2), 1e-5)
+
+
+def test_roi_align_crowded_band_and_tile(roi_path):
     """1200 RoIs in one corner of one image (600 of them identical): one band / one tile carries far more RoIs than a
     shared-memory table chunk or a message batch holds; the identical RoIs make the backward accumulate 600 times
     into the same pixels (order-dependent rounding: 1e-4 relative still holds)."""
@@ -822,7 +846,7 @@ def test_nms_threshold_extremes_and_identical_boxes():
             assert int(num.item()) == len(ref) and np.array_equal(N(keep)[: len(ref)], ref), (thr, delta)
 
 
-def test_roi_align_rois_outside_inverted_and_whole_image():
+def test_roi_align_rois_outside_inverted_and_whole_image(roi_path):
     """RoIs that miss the map, inverted corners (width / height clamp to 1), RoIs larger than the map, single-pixel RoIs:
     the planners reject what does not fit their windows and the gather path takes over - same numbers either way."""
     from mxdetection_b200.ops import roi_align_fpn_forward, roi_align_fpn_backward
