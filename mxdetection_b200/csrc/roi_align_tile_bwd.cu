@@ -28,8 +28,11 @@
 
 namespace mxd {
 
-constexpr int kTbWarps = 31;                       // consumer warps; warp w owns tile row w
-constexpr int kTbThreads = (kTbWarps + 1) * 32;    // + one producer warp
+constexpr int kTbWarps = 25;                       // consumer warps; warp w owns tile row w (a tile has at most 25 rows)
+constexpr int kTbProducers = 4;                    // producer warps: message m is built by producer m mod 4 (one warp needs
+                                                   // ~1500 cycles per message - two bulk copies, a barrier wait, the packed
+                                                   // bins - and left the consumers waiting 30 % of the time)
+constexpr int kTbThreads = (kTbWarps + kTbProducers) * 32;
 constexpr int kTbMaxStages = 16;                   // ring depth is per configuration (9 for 7x7, 4 for 14x14)
 constexpr int kTbMaxHfCap = 256;                   // rows of the dense per-RoI row table: min(cap, tallest map)
 constexpr int kTbPix = 33;                         // words per tile pixel (32 channels + 1 pad)
@@ -39,6 +42,7 @@ constexpr int kTbMaxTw = 48;
 constexpr int kTbRowWords = (kTbMaxTw + 1) * kTbPix;   // fixed row pitch: 48 columns + the trash column
 constexpr int kTbTrash = kTbMaxTw * kTbPix * 4;        // byte offset of the trash pixel inside a row
 constexpr int kTbSmem = 227 * 1024;
+constexpr int kTbCtlBytes = 384;                   // TbCtl
 
 enum { kMsgPair = 0, kMsgBegin = 1, kMsgZero = 2, kMsgStop = 3 };
 
@@ -97,7 +101,7 @@ static bool make_tcfg(int N, int C, int L, const int* Hs, const int* Ws, int PH,
   c->off_g = c->off_rt + kTbMaxTh * 32;
   c->stage_bytes = (int)align_up((size_t)c->off_g + 32 * c->bins * 4, 128);
   c->n_stages = PW == 7 ? 9 : 4;                    // 7.5 KB / 26 KB of grad_out per stage
-  c->tile_bytes = (kTbSmem - c->n_stages * c->stage_bytes - 256) & ~15;
+  c->tile_bytes = (kTbSmem - c->n_stages * c->stage_bytes - kTbCtlBytes) & ~15;
   const int max_rows = c->tile_bytes / (kTbRowWords * 4);
   c->max_rows = max_rows;
   int base = 0;
@@ -120,7 +124,7 @@ static bool make_tcfg(int N, int C, int L, const int* Hs, const int* Ws, int PH,
   c->ncg = C / 32;
   if ((long long)c->NT * c->ncg > 0x3fffffffLL) return false;
   c->n_items = c->NT * c->ncg;
-  c->smem_bytes = c->tile_bytes + c->n_stages * c->stage_bytes + 256;
+  c->smem_bytes = c->tile_bytes + c->n_stages * c->stage_bytes + kTbCtlBytes;
   return c->NT > 0;
 }
 
@@ -277,7 +281,9 @@ __global__ void __launch_bounds__(1024) tplan_group_kernel(TCfg c, TWs w, int R)
 struct TbCtl {
   u64 full[kTbMaxStages];
   u64 empty[kTbMaxStages];
+  int items[2];          // item ids, written by producer 0 and read by the others (double-buffered)
 };
+static_assert(sizeof(TbCtl) <= kTbCtlBytes, "control block");
 
 // The 4 x taps of bin pw (2 samples x lo/hi) as up to 4 DISTINCT tile columns with merged weights
 // (already scaled by 1/count), so the consumer can issue the 4 loads before the 4 stores.  Columns
@@ -298,19 +304,31 @@ __device__ __forceinline__ uint4 tb_pack_bin(uint4 e, int tx0, int tw, float inv
                     col(c0) | (col(c1) << 8) | (col(c2) << 16) | (col(c3) << 24));
 }
 
+// Producer p of kTbProducers.  All producers walk the same sequence of items (producer 0 pulls the item id off the
+// global counter and passes it on through shared memory, one named barrier per item) and therefore number the messages
+// alike; producer p builds the messages m = p mod kTbProducers into stage m mod n_stages.
 __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, const TWs& w,
                                             const float* __restrict__ gout, unsigned char* stages, TbCtl* ctl,
-                                            int lane) {
+                                            int lane, int p) {
   const unsigned full = 0xffffffffu;
+  constexpr int P = kTbProducers;
   const int S = c.n_stages;
-  int s = 0;
+  int m = 0;            // messages issued so far by all producers
+  int s = p % S;        // stage of this producer's next message (message number == p mod P)
   uint32_t par = 1;     // parity to wait for on empty[s]: the first pass over the ring succeeds at once
-  auto advance = [&]() { if (++s == S) { s = 0; par ^= 1u; } };
+  int mine = p;         // number of this producer's next message
+  auto advance = [&]() { mine += P; s += P; if (s >= S) { s -= S; par ^= 1u; } };
   const uint32_t g_bytes = (uint32_t)(32 * c.bins * 4);
-  for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(&w.hdr[0], 1);
-    item = __shfl_sync(full, item, 0);
+#ifdef MXD_TB_PROF
+  long long t_emp = 0, t_all = clock64();
+#define TB_WAIT_EMPTY() { const long long _t = clock64(); mbar_wait(&ctl->empty[s], par); t_emp += clock64() - _t; }
+#else
+#define TB_WAIT_EMPTY() mbar_wait(&ctl->empty[s], par)
+#endif
+  for (int it = 0;; ++it) {
+    if (p == 0 && lane == 0) ctl->items[it & 1] = atomicAdd(&w.hdr[0], 1);
+    asm volatile("bar.sync 2, %0;" ::"n"(32 * kTbProducers) : "memory");
+    const int item = ctl->items[it & 1];
     if (item >= c.n_items) break;
     // Items are level-major, coarsest level first (its tiles carry the most RoIs: heavy items early, light ones
     // fill the tail); inside a level all tiles of one (image, channel group) are neighbours, so the RoIs'
@@ -331,8 +349,8 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
     const int tile_id = b * c.tiles_per_img + t;
     const int cnt = w.cnt[tile_id], start = w.start[tile_id];
     if (cnt == 0 && c.accumulate) continue;    // req=add and nothing to add
-    {
-      mbar_wait(&ctl->empty[s], par);
+    if (mine == m) {                           // the item's first message: begin (RoIs follow) or zero (write zeros)
+      TB_WAIT_EMPTY();
       if (lane == 0) {
         int* hd = reinterpret_cast<int*>(stages + (size_t)s * c.stage_bytes);
         hd[0] = cnt ? kMsgBegin : kMsgZero;
@@ -341,50 +359,65 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
       }
       advance();
     }
-    for (int base = 0; base < cnt; base += 32) {
-      const int nb = min(32, cnt - base);
-      const int my_n = lane < nb ? w.pairs[start + base + lane] : 0;
+    ++m;
+    // pairs j = j0, j0 + P, ... of this item are mine; 32 of them are looked up at a time (lane i: pair j0 + i * P)
+    for (int j0 = mine - m; j0 < cnt; j0 += 32 * P) {
+      const int jl = j0 + lane * P;
+      const int my_n = jl < cnt ? w.pairs[start + jl] : 0;
       const int4 h0 = w.roihdr[(size_t)my_n * 2];
-      if (lane < nb)   // the slices of the next 32 pairs start their trip HBM -> L2 now
+      if (jl < cnt)   // the slices of my next pairs start their trip HBM -> L2 now
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gout + ((size_t)my_n * c.C + cg * 32) * c.bins),
                      "r"(g_bytes)
                      : "memory");
+      const int nb = min(32, (cnt - j0 + P - 1) / P);
       uint4 xe = make_uint4(0u, 0u, 0u, 0u);      // lane pw: samples 2pw, 2pw+1 of the next pair's RoI
       {
         const int n0 = __shfl_sync(full, my_n, 0);
         if (lane < c.PW) xe = reinterpret_cast<const uint4*>(w.xtab + (size_t)n0 * c.tx)[lane];
       }
-      for (int j = 0; j < nb; ++j) {
-        const int n = __shfl_sync(full, my_n, j);
-        const int y0 = __shfl_sync(full, h0.x, j), Hf = __shfl_sync(full, h0.y, j);
+      for (int q = 0; q < nb; ++q) {
+        const int n = __shfl_sync(full, my_n, q);
+        const int y0 = __shfl_sync(full, h0.x, q), Hf = __shfl_sync(full, h0.y, q);
         const uint4 xc = xe;
-        if (j + 1 < nb) {
-          const int n1 = __shfl_sync(full, my_n, j + 1);
+        if (q + 1 < nb) {
+          const int n1 = __shfl_sync(full, my_n, q + 1);
           if (lane < c.PW) xe = reinterpret_cast<const uint4*>(w.xtab + (size_t)n1 * c.tx)[lane];
         }
-        mbar_wait(&ctl->empty[s], par);
+        TB_WAIT_EMPTY();
         unsigned char* st = stages + (size_t)s * c.stage_bytes;
         const int ra = max(y0, ty0) - ty0;
         const int rb = min(y0 + Hf - 1, ty0 + v.th - 1) - ty0;
         if (lane < c.PW) reinterpret_cast<uint4*>(st + c.off_xt)[lane] = tb_pack_bin(xc, tx0, v.tw, c.inv_count);
-        if (lane == 0) reinterpret_cast<int*>(st)[0] = kMsgPair | (ra << 8) | (rb << 16);
-        __syncwarp();
+        const uint32_t rt_bytes = (uint32_t)((rb - ra + 1) * 32);
         if (lane == 0) {
-          const uint32_t rt_bytes = (uint32_t)((rb - ra + 1) * 32);
+          reinterpret_cast<int*>(st)[0] = kMsgPair | (ra << 8) | (rb << 16);
           mbar_arrive_expect_tx(&ctl->full[s], g_bytes + rt_bytes);
+        }
+        __syncwarp();
+        // lane 0 copies the grad_out slice, lane 1 the row-table slice: one instruction issues both
+        if (lane == 0)
           bulk_g2s(st + c.off_g, gout + ((size_t)n * c.C + cg * 32) * c.bins, g_bytes, &ctl->full[s]);
+        else if (lane == 1)
           bulk_g2s(st + c.off_rt + ra * 32, w.rowtab + ((size_t)n * c.max_hf + (ra + ty0 - y0)) * 2, rt_bytes,
                    &ctl->full[s]);
-        }
         advance();
       }
     }
+    m += cnt;
   }
-  mbar_wait(&ctl->empty[s], par);
-  if (lane == 0) {
-    reinterpret_cast<int*>(stages + (size_t)s * c.stage_bytes)[0] = kMsgStop;
-    mbar_arrive(&ctl->full[s]);
+  if (mine == m) {
+    TB_WAIT_EMPTY();
+    if (lane == 0) {
+      reinterpret_cast<int*>(stages + (size_t)s * c.stage_bytes)[0] = kMsgStop;
+      mbar_arrive(&ctl->full[s]);
+    }
   }
+#ifdef MXD_TB_PROF
+  if (lane == 0 && p == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(w.hdr + 16), (unsigned long long)t_emp);
+    atomicAdd(reinterpret_cast<unsigned long long*>(w.hdr + 18), (unsigned long long)(clock64() - t_all));
+  }
+#endif
 }
 
 // One tile row of one RoI for this lane's channel: h[pw] = sum_ph Wy[row][ph] * g[ph][pw], then the
@@ -484,8 +517,8 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
     fence_mbar_init();
   }
   __syncthreads();
-  if (warp == kTbWarps) {
-    tb_producer(d, c, w, gout, stages, ctl, lane);
+  if (warp >= kTbWarps) {
+    tb_producer(d, c, w, gout, stages, ctl, lane, warp - kTbWarps);
     return;
   }
   // ================================= consumer warps ====================================
@@ -534,21 +567,46 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
     }
     __syncwarp();
   };
+#ifdef MXD_TB_PROF
+  long long t_full = 0, t_row = 0, t_wr = 0, t_call = clock64();
+#endif
   for (;;) {
+#ifdef MXD_TB_PROF
+    { const long long _t = clock64(); mbar_wait(&ctl->full[s], par); t_full += clock64() - _t; }
+#else
     mbar_wait(&ctl->full[s], par);
+#endif
     const unsigned char* st = stages + (size_t)s * c.stage_bytes;
     const int hd = reinterpret_cast<const int*>(st)[0];
     const int kind = hd & 0xff;
     if (kind == kMsgPair) {
       if (warp >= ((hd >> 8) & 0xff) && warp <= (hd >> 16)) {
         touched = true;
+#ifdef MXD_TB_PROF
+        const long long _t = clock64();
+#endif
         tb_row<PW>(reinterpret_cast<const float*>(st + c.off_g) + lane * c.bins,
                    reinterpret_cast<const uint2*>(st + c.off_rt) + warp * 4,
                    reinterpret_cast<const uint4*>(st + c.off_xt), reinterpret_cast<char*>(trow + lane),
                    2.0f * c.inv_count);
+#ifdef MXD_TB_PROF
+        t_row += clock64() - _t;
+#endif
       }
     } else {
+#ifdef MXD_TB_PROF
+      const long long _t = clock64();
+#endif
       if (have) write_row(!touched);     // an untouched row is still all zero: store zeros, skip the LDS / STS pass
+#ifdef MXD_TB_PROF
+      t_wr += clock64() - _t;
+      if (kind == kMsgStop && lane == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(w.hdr + 20), (unsigned long long)t_full);
+        atomicAdd(reinterpret_cast<unsigned long long*>(w.hdr + 22), (unsigned long long)t_row);
+        atomicAdd(reinterpret_cast<unsigned long long*>(w.hdr + 24), (unsigned long long)t_wr);
+        atomicAdd(reinterpret_cast<unsigned long long*>(w.hdr + 26), (unsigned long long)(clock64() - t_call));
+      }
+#endif
       have = false; touched = false;
       if (kind == kMsgStop) break;
       const int4 h1 = reinterpret_cast<const int4*>(st)[1];
@@ -576,6 +634,12 @@ __global__ void __launch_bounds__(256) tile_bwd_fallback_kernel(FpnDesc d, TCfg 
     gather_roi_chunk<true>(d, g, n, c0, min(32, c.C - c0), gout, c.PH, c.PW, threadIdx.x, 256);
   }
 }
+
+#ifdef MXD_TB_PROF
+extern "C" int mxd_tb_prof(const void* ws, unsigned long long* out6) {
+  return (int)cudaMemcpy(out6, (const char*)ws + 64, 48, cudaMemcpyDeviceToHost);
+}
+#endif
 
 size_t tile_bwd_workspace_bytes(int R, int N, int L, const int* Hs, const int* Ws, int C, int PH, int PW, int sr) {
   TCfg c;

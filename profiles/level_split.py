@@ -34,11 +34,12 @@ def timed(fn, n=10):
 
 
 res = {}
-for name, sel in [("all", np.ones(len(lv), bool))] + [("L%d" % l, lv == l) for l in range(4)]:
+for name, sel in [("all", np.ones(len(lv), bool)), ("none", np.zeros(len(lv), bool))] + [("L%d" % l, lv == l) for l in range(4)]:
     rois = rois_all[torch.from_numpy(np.nonzero(sel)[0]).to(dev)].contiguous()
     gout = torch.randn((rois.shape[0], 256, 7, 7), device=dev)
     out = torch.empty_like(gout)
     f = timed(lambda: roi_align_fpn_forward(feats, rois, (7, 7), d["scales"], 2, out=out))
     b = timed(lambda: roi_align_fpn_backward(gout, rois, shapes, (7, 7), d["scales"], 2, grad_feats=grads, accumulate=True))
-    res[name] = {"rois": int(rois.shape[0]), "fwd_ms": f, "bwd_add_ms": b}
+    bw = timed(lambda: roi_align_fpn_backward(gout, rois, shapes, (7, 7), d["scales"], 2, grad_feats=grads, accumulate=False))
+    res[name] = {"rois": int(rois.shape[0]), "fwd_ms": f, "bwd_add_ms": b, "bwd_write_ms": bw}
 print(json.dumps(res))
