@@ -42,7 +42,7 @@ extern "C" {
 
 #define MXD_MAX_LEVELS 8    /* FPN levels per call                               */
 #define MXD_MAX_BASE_ANCHORS 16
-#define MXD_SORT_CAP 8192   /* max rows sorted inside one CTA (top-k / NMS)      */
+#define MXD_SORT_CAP 8192   /* rows sorted inside one CTA; longer top-k / NMS take the chunked path */
 
 /* ---- library ------------------------------------------------------------ */
 int mxd_version(void);                /* 10000*major + 100*minor + patch        */
@@ -96,8 +96,9 @@ int mxd_roi_align_fpn_backward(const DLTensor* grad_out, const DLTensor* rois,
  *      mx.nd.contrib.box_nms, Spec B: strict iou > thr, stable score-desc /
  *      index-asc order) ---------------------------------------------------- */
 /* Stable top-k: scores (S,n) f32 -> idx (S,k) i32, vals (S,k) f32 sorted by
- * (score desc, index asc); k = min(topk,n) (topk<=0: k=n).  Needs k <=
- * MXD_SORT_CAP.                                                               */
+ * (score desc, index asc); k = min(topk,n) (topk<=0: k=n).  k <= MXD_SORT_CAP
+ * is sorted inside one CTA / cluster; larger k takes a chunk-sort + rank-merge
+ * path that needs the workspace mxd_topk_stable_workspace_bytes reports.        */
 size_t mxd_topk_stable_workspace_bytes(int segments, int n, int topk);
 int mxd_topk_stable(const DLTensor* scores, DLTensor* idx, DLTensor* vals, int topk,
                     void* workspace, size_t workspace_bytes, void* stream);
@@ -111,6 +112,15 @@ int mxd_nms(const DLTensor* boxes, const DLTensor* scores, const DLTensor* ids,
             DLTensor* keep, DLTensor* num_keep, float iou_thr, float delta, int topk,
             float valid_thresh, int force_suppress, int max_out,
             void* workspace, size_t workspace_bytes, void* stream);
+/* Batched form over ragged segments of ONE (n,4) / (n) pair (e.g. the (image, level) segments of the proposal
+ * stage): segment s = rows [seg_offsets[s], seg_offsets[s+1]); seg_offsets (S+1) i32 ascending, on the device;
+ * max_seg_len = host upper bound of the longest segment (sizes the workspace).  keep (S,cap) i32 receives GLOBAL row
+ * indices in score order, -1 padded; num_keep (S) i32.  Other arguments as mxd_nms, applied per segment.            */
+size_t mxd_nms_batched_workspace_bytes(int num_segments, int max_seg_len, int topk);
+int mxd_nms_batched(const DLTensor* boxes, const DLTensor* scores, const DLTensor* ids,
+                    const DLTensor* seg_offsets, int max_seg_len, DLTensor* keep, DLTensor* num_keep,
+                    float iou_thr, float delta, int topk, float valid_thresh, int force_suppress,
+                    int max_out, void* workspace, size_t workspace_bytes, void* stream);
 /* MXNet tensor form: data (B,N,K) f32 -> out (B,N,K) kept rows first (score
  * order), all other rows -1; index (B,N) i32 or NULL receives the source row of
  * each output row (-1 for padding) - the record box_nms' backward consumes.
@@ -244,7 +254,7 @@ int mxd_rpn_proposals_stages(const mxd_rpn_config* cfg, int batch, const void* w
  * cls_prob (N,2A,H,W) f32 [foreground = channels A..2A-1], bbox_pred (N,4A,H,W), im_info (N,3)
  * [height,width,scale] -> rois (N*post_n,5) [batch,x1,y1,x2,y2] and, when not NULL, scores (N*post_n,1);
  * rows beyond the kept boxes repeat them cyclically as mxnet does.  base_anchors: host float[A*4]
- * (utils::GenerateAnchors table).  rpn_pre_nms_top_n <= 0 = all (at most 8192 rows are sorted).      */
+ * (utils::GenerateAnchors table).  rpn_pre_nms_top_n <= 0 = all.                                     */
 size_t mxd_multi_proposal_workspace_bytes(int batch, int num_anchors, int feat_h, int feat_w,
                                           int rpn_pre_nms_top_n, int rpn_post_nms_top_n);
 int mxd_multi_proposal(const DLTensor* cls_prob, const DLTensor* bbox_pred, const DLTensor* im_info,

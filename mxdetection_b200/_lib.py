@@ -71,7 +71,7 @@ def _load():
 lib = _load()
 lib.mxd_last_error.restype = c_char_p
 lib.mxd_launch_count.restype = c_uint64
-for _n in ("mxd_topk_stable_workspace_bytes", "mxd_nms_workspace_bytes", "mxd_box_nms_workspace_bytes",
+for _n in ("mxd_topk_stable_workspace_bytes", "mxd_nms_workspace_bytes", "mxd_nms_batched_workspace_bytes", "mxd_box_nms_workspace_bytes",
            "mxd_max_iou_assign_workspace_bytes", "mxd_rpn_proposals_workspace_bytes",
            "mxd_roi_align_workspace_bytes", "mxd_multi_proposal_workspace_bytes", "mxd_random_sample_workspace_bytes", "mxd_det_bboxes_workspace_bytes"):
     if hasattr(lib, _n):
@@ -163,6 +163,8 @@ _SIG = {
     "mxd_topk_stable": [_P, _P, _P, c_int, _P, c_size_t, _P],
     "mxd_nms_workspace_bytes": [c_int, c_int],
     "mxd_nms": [_P, _P, _P, _P, _P, c_float, c_float, c_int, c_float, c_int, c_int, _P, c_size_t, _P],
+    "mxd_nms_batched_workspace_bytes": [c_int, c_int, c_int],
+    "mxd_nms_batched": [_P, _P, _P, _P, c_int, _P, _P, c_float, c_float, c_int, c_float, c_int, c_int, _P, c_size_t, _P],
     "mxd_box_nms_workspace_bytes": [c_int, c_int, c_int],
     "mxd_box_nms": [_P, _P, _P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P],
     "mxd_box_nms_backward": [_P, _P, _P, _P],

@@ -12,9 +12,11 @@ struct TopkParams {
   long long seg_stride[MXD_MAX_LEVELS];
   int elem_stride;
   int n[MXD_MAX_LEVELS];
-  int k[MXD_MAX_LEVELS];                // min(topk, n) per level, <= MXD_SORT_CAP
+  int k[MXD_MAX_LEVELS];                // min(topk, n) per level (above MXD_SORT_CAP: chunk-sort + rank-merge path)
   int kmax;                             // row stride of the outputs
   float valid_thresh;                   // rows with score <= valid_thresh are dropped (-inf: none)
+  const int* seg_off;                   // optional (device, S+1): ragged segments of ONE score array (num_levels 1):
+                                        // segment s = scores[0][seg_off[s] .. seg_off[s+1]), n[0] / k[0] = upper bounds
   int* out_idx;                         // (S,kmax) i32, -1 padded
   float* out_val;                       // (S,kmax) f32 or null
   int* out_cnt;                         // (S) i32 or null: number of real rows
@@ -31,7 +33,9 @@ struct TopkParams {
   float max_ratio;
   float min_size;
 };
-int launch_topk(const TopkParams& p, cudaStream_t st);
+// long_ws: scratch of topk_long_workspace_bytes(S, max n, max k) bytes, needed only when some k exceeds MXD_SORT_CAP
+int launch_topk(const TopkParams& p, cudaStream_t st, void* long_ws = nullptr, size_t long_ws_bytes = 0);
+size_t topk_long_workspace_bytes(int S, long long n_max, int k_max);
 
 // ---- NMS over score-sorted segments ---------------------------------------------
 struct NmsSortedArgs {

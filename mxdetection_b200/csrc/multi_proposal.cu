@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(256) mxp_output_kernel(const float4* __restric
 
 struct MxpWs {
   float4* boxes; float* scores; int* idx; float* vals; int* cnt; float4* sorted; u64* mask; int* keep; int* keep_cnt;
+  void* sortws; size_t sort_bytes;      // chunk-sort scratch when rpn_pre_nms_top_n exceeds MXD_SORT_CAP
   size_t bytes;
 };
 
@@ -125,6 +126,8 @@ static MxpWs carve_mxp(void* base, int B, int n, int k, int post_n) {
   w.mask = (u64*)take(sizeof(u64) * nms_mask_words(B, k));
   w.keep = (int*)take(sizeof(int) * (size_t)B * post_n);
   w.keep_cnt = (int*)take(sizeof(int) * (size_t)B);
+  w.sort_bytes = topk_long_workspace_bytes(B, n, k);
+  w.sortws = take(w.sort_bytes);
   w.bytes = off;
   return w;
 }
@@ -135,7 +138,6 @@ static int mxp_dims(int A, int H, int W, int pre_n, int post_n, int* n, int* k) 
   MXD_REQUIRE(post_n >= 1, MXD_EINVAL, "rpn_post_nms_top_n must be >= 1");
   *n = H * W * A;
   *k = (pre_n > 0 && pre_n < *n) ? pre_n : *n;
-  MXD_REQUIRE(*k <= MXD_SORT_CAP, MXD_ENOTSUP, "rpn_pre_nms_top_n %d exceeds the in-CTA sort capacity %d", *k, MXD_SORT_CAP);
   return MXD_OK;
 }
 
@@ -195,7 +197,7 @@ int mxd_multi_proposal(const DLTensor* cls_prob, const DLTensor* bbox_pred, cons
   p.scores[0] = w.scores; p.seg_stride[0] = n; p.n[0] = n; p.k[0] = k;
   p.valid_thresh = -INFINITY;
   p.out_idx = w.idx; p.out_val = w.vals; p.out_cnt = w.cnt;
-  if ((rc = launch_topk(p, st))) return rc;
+  if ((rc = launch_topk(p, st, w.sortws, w.sort_bytes))) return rc;
   mxp_gather_kernel<<<dim3((k + 255) / 256, B), 256, 0, st>>>(w.boxes, w.idx, n, k, w.sorted);
   MXD_POST_LAUNCH("multi_proposal_gather");
 

@@ -11,7 +11,8 @@
 //   fixed point on the transposed diagonal words; the other warps fold the kept rows' words into the suppression
 //   words of the later blocks one step behind; bands arrive by bulk copies on an mbarrier ring.  Nothing leaves
 //   the device (MXNet's MultiProposal copies the mask to the host for this step).
-//   nms_resolve_kernel (row-major mask, shared-memory atomics) remains for segments too long for the scan kernel.
+//   nms_resolve_global_kernel (row-major mask read from L2) takes segments too long for the scan kernel's ring.
+#include <stdlib.h>
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -87,28 +88,17 @@ __global__ void __launch_bounds__(64 * kMaskRowBlocks) nms_mask_kernel(NmsSorted
   }
 }
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// Resolve kernel for segments too long for the scan kernel's shared-memory ring (> ~9400 boxes): one CTA per
+// segment, the row-major mask stays in global memory (L2), only the suppression words live in shared memory.  Per
+// block of 64 boxes warp 0 walks the diagonal words (64-step chain), then every thread ORs the kept rows' words into
+// the suppression words it owns (column w belongs to thread w mod 1024: no atomics).  O(n^2 / 64) words through L2 -
+// the price of a segment that mx.nd.contrib.box_nms would resolve with n sequential launches.
+constexpr int kResolveThreads = 1024;
 
-// One CTA (8 warps) per segment.  The greedy scan is sequential in the 64-box blocks, so everything else is taken
-// off that chain: the mask rows of the NEXT block are prefetched into shared memory with cp.async by all threads
-// while the current block is resolved; warp 0 alone resolves the 64x64 diagonal block (64 independent shuffles,
-// then a 64-step register chain); the kept rows' suppression words for the later blocks are OR-ed in by all
-// eight warps (8 rows each, 64-bit shared-memory atomics).  One warp doing all of it measured 171 us for
-// 2000 boxes (0.18 IPC, pure dependent-load latency).
-constexpr int kResolveThreads = 256;
-
-__global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(NmsSortedArgs a, int W) {
-  extern __shared__ u64 sm[];   // remv[W] | band[2][64][W]
+__global__ void __launch_bounds__(kResolveThreads) nms_resolve_global_kernel(NmsSortedArgs a, int W) {
+  extern __shared__ u64 remv[];   // [W]
   __shared__ u64 s_keep;
   __shared__ int s_done;
-  u64* remv = sm;
-  u64* band = sm + W;
   const int s = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.counts ? min(a.counts[s], a.n_max) : a.n_max;
@@ -125,34 +115,15 @@ __global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(NmsSortedA
     const u64 d = (u64)__ballot_sync(0xffffffffu, dead0) | ((u64)__ballot_sync(0xffffffffu, dead1) << 32);
     if (lane == 0) remv[w] = d;
   }
-  // words [j, nW) of the rows of block j -> band[j&1]
-  auto prefetch = [&](int j) {
-    u64* dst = band + (size_t)(j & 1) * 64 * W;
-    const int nw = nW - j;
-    const int rows = min(64, n - j * 64);
-    for (int t = tid; t < rows * nw; t += kResolveThreads) {
-      const int i = t / nw, w = j + (t - i * nw);
-      cp_async8(dst + (size_t)i * W + w, mask + (size_t)(j * 64 + i) * W + w);
-    }
-    cp_async_commit();
-  };
-  if (nW > 0) prefetch(0);
   if (tid == 0) s_done = 0;
+  __syncthreads();
   int nkeep = 0;               // tracked by warp 0
   for (int j = 0; j < nW; ++j) {
-    if (j + 1 < nW) {
-      prefetch(j + 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();           // band j landed for every thread; remv[j] is final
-    const u64* bj = band + (size_t)(j & 1) * 64 * W;
     if (warp == 0) {
       const int r0 = j * 64 + lane, r1 = r0 + 32;
       u64 cur = remv[j];
-      const u64 wlo = (r0 < n) ? bj[(size_t)lane * W + j] : 0ull;
-      const u64 whi = (r1 < n) ? bj[(size_t)(lane + 32) * W + j] : 0ull;
+      const u64 wlo = (r0 < n) ? mask[(size_t)r0 * W + j] : 0ull;
+      const u64 whi = (r1 < n) ? mask[(size_t)r1 * W + j] : 0ull;
       u64 keepbits = 0;
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
@@ -184,20 +155,18 @@ __global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(NmsSortedA
     }
     __syncthreads();
     if (s_done) break;
-    const u64 keepbits = s_keep;
-    const unsigned mine = (unsigned)(keepbits >> (warp * 8)) & 0xffu;     // this warp's 8 rows of the block
-    if (mine) {
-      for (int w = j + 1 + lane; w < nW; w += 32) {
-        u64 acc = 0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-          if ((mine >> r) & 1u) acc |= bj[(size_t)(warp * 8 + r) * W + w];
-        if (acc) atomicOr(reinterpret_cast<unsigned long long*>(&remv[w]), acc);
+    u64 kb = s_keep;
+    for (int w = j + 1 + tid; w < nW; w += kResolveThreads) {
+      u64 acc = 0, bits = kb;
+      while (bits) {
+        const int r = __ffsll((long long)bits) - 1;
+        bits &= bits - 1;
+        acc |= mask[(size_t)(j * 64 + r) * W + w];
       }
+      if (acc) remv[w] |= acc;
     }
-    __syncthreads();           // remv complete, band[j&1] free for the prefetch of block j+2
+    __syncthreads();
   }
-  cp_async_wait<0>();
   __syncthreads();
   if (warp == 0) {
     for (int i = nkeep + lane; i < a.keep_stride; i += 32) keep[i] = -1;
@@ -372,12 +341,13 @@ int launch_nms_sorted(const NmsSortedArgs& a, cudaStream_t st) {
   if (a.S == 0) return MXD_OK;
   const int W = (a.n_max + 63) / 64;
   // scan kernel (band-major mask) with a 3- to 8-buffer band ring when it fits shared memory, else the row-major
-  // atomic resolve kernel (segments above ~9400 boxes)
+  // mask + global-memory resolve kernel (segments above ~9400 boxes)
   constexpr int kResolveSmemMax = 226 * 1024;      // 227 KB per CTA minus the kernels' static shared variables
   const size_t Wz = (size_t)(W > 0 ? W : 1);
   int slots = 0;
   for (int sl = kScanMaxSlots; sl >= 3 && !slots; --sl)     // ring depth: the L2 -> shared latency (~1 us) spans several blocks
     if ((Wz * 4 + (Wz + 1) * 64 * (size_t)sl) * sizeof(u64) <= (size_t)kResolveSmemMax) slots = sl;
+  if (getenv("MXD_NMS_FORCE_GLOBAL") != nullptr) slots = 0;          // (tests force the long-segment path)
   if (a.n_max > 0) {
     MXD_REQUIRE(a.S <= 65535 && W <= 65535, MXD_ENOTSUP, "too many NMS segments");
     dim3 grid(W, (W + kMaskRowBlocks - 1) / kMaskRowBlocks, a.S);
@@ -388,17 +358,17 @@ int launch_nms_sorted(const NmsSortedArgs& a, cudaStream_t st) {
   static unsigned long long seen = 0;
   if (first_use_on_device(&seen)) {
     MXD_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResolveSmemMax));
-    MXD_CUDA_OK(cudaFuncSetAttribute(nms_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResolveSmemMax));
+    MXD_CUDA_OK(cudaFuncSetAttribute(nms_resolve_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResolveSmemMax));
   }
   if (slots) {
     nms_scan_kernel<<<a.S, kScanThreads, (Wz * 4 + (Wz + 1) * 64 * (size_t)slots) * sizeof(u64), st>>>(a, W, slots);
     MXD_POST_LAUNCH("nms_scan");
     return MXD_OK;
   }
-  const size_t smem = Wz * (1 + 2 * 64) * sizeof(u64);
+  const size_t smem = Wz * sizeof(u64);
   MXD_REQUIRE(smem <= (size_t)kResolveSmemMax, MXD_ENOTSUP, "NMS segment of %d boxes exceeds the resolve kernel's shared memory", a.n_max);
-  nms_resolve_kernel<<<a.S, kResolveThreads, smem, st>>>(a, W);
-  MXD_POST_LAUNCH("nms_resolve");
+  nms_resolve_global_kernel<<<a.S, kResolveThreads, smem, st>>>(a, W);
+  MXD_POST_LAUNCH("nms_resolve_global");
   return MXD_OK;
 }
 
@@ -413,6 +383,28 @@ __global__ void nms_gather_kernel(const float* __restrict__ boxes, const int* __
   if (i >= 0) b = reinterpret_cast<const float4*>(boxes)[i];
   ob[j] = b;
   if (oid) oid[j] = (i >= 0 && ids) ? ids[i] : 0;
+}
+
+// Ragged segments: order (S,kmax) holds positions inside the segment; boxes / ids are gathered into score order and the
+// positions are turned into GLOBAL row indices (what the keep list reports).
+__global__ void nms_gather_seg_kernel(const float* __restrict__ boxes, const int* __restrict__ ids,
+                                      const int* __restrict__ seg_off, int* __restrict__ order, int kmax,
+                                      float4* __restrict__ ob, int* __restrict__ oid) {
+  const int s = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= kmax) return;
+  const size_t o = (size_t)s * kmax + j;
+  const int i = order[o];
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  int id = 0;
+  if (i >= 0) {
+    const int gi = seg_off[s] + i;
+    b = reinterpret_cast<const float4*>(boxes)[gi];
+    if (ids) id = ids[gi];
+    order[o] = gi;
+  }
+  ob[o] = b;
+  if (oid) oid[o] = id;
 }
 
 // ---- MXNet (B,N,K) tensor form ------------------------------------------------
@@ -522,10 +514,11 @@ __global__ void det_output_kernel(const float4* __restrict__ cb, const float* __
 
 struct NmsWs {
   int* order; float* vals; int* cnt; float4* boxes; int* ids; u64* mask; int* keep; int* keep_cnt;
+  void* sortws; size_t sort_bytes;       // chunk-sort scratch, only when kmax exceeds MXD_SORT_CAP
   size_t bytes;
 };
 
-static NmsWs carve(void* base, int S, int kmax) {
+static NmsWs carve(void* base, int S, int kmax, long long n = 0) {
   NmsWs w;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (char*)base + o; };
@@ -537,6 +530,8 @@ static NmsWs carve(void* base, int S, int kmax) {
   w.mask = (u64*)take(sizeof(u64) * nms_mask_words(S, kmax));
   w.keep = (int*)take(sizeof(int) * (size_t)S * kmax);
   w.keep_cnt = (int*)take(sizeof(int) * (size_t)S);
+  w.sort_bytes = topk_long_workspace_bytes(S, n, kmax);
+  w.sortws = take(w.sort_bytes);
   w.bytes = off;
   return w;
 }
@@ -549,7 +544,7 @@ using namespace mxd;
 
 extern "C" {
 
-size_t mxd_nms_workspace_bytes(int n, int topk) { return carve(nullptr, 1, eff_k(n, topk)).bytes; }
+size_t mxd_nms_workspace_bytes(int n, int topk) { return carve(nullptr, 1, eff_k(n, topk), n).bytes; }
 
 int mxd_nms(const DLTensor* boxes, const DLTensor* scores, const DLTensor* ids, DLTensor* keep,
             DLTensor* num_keep, float iou_thr, float delta, int topk, float valid_thresh,
@@ -575,9 +570,7 @@ int mxd_nms(const DLTensor* boxes, const DLTensor* scores, const DLTensor* ids, 
     MXD_CUDA_OK(cudaMemsetAsync(dptr<int>(num_keep), 0, sizeof(int), st));
       return MXD_OK;
   }
-  MXD_REQUIRE(k <= MXD_SORT_CAP, MXD_ENOTSUP,
-              "NMS over %d rows exceeds the in-CTA sort capacity %d (pass topk)", k, MXD_SORT_CAP);
-  NmsWs w = carve(workspace, 1, k);
+  NmsWs w = carve(workspace, 1, k, n);
   MXD_REQUIRE(workspace && workspace_bytes >= w.bytes, MXD_EWORKSPACE, "workspace %zu < %zu bytes",
               workspace_bytes, w.bytes);
   TopkParams p = {};
@@ -586,7 +579,7 @@ int mxd_nms(const DLTensor* boxes, const DLTensor* scores, const DLTensor* ids, 
   p.n[0] = (int)n; p.k[0] = k; p.kmax = k;
   p.valid_thresh = valid_thresh;
   p.out_idx = w.order; p.out_val = nullptr; p.out_cnt = w.cnt;
-  if ((rc = launch_topk(p, st))) return rc;
+  if ((rc = launch_topk(p, st, w.sortws, w.sort_bytes))) return rc;
   const bool class_aware = ids && !force_suppress;
   nms_gather_kernel<<<(k + 255) / 256, 256, 0, st>>>(dptr<float>(boxes), ids ? dptr<int>(ids) : nullptr, w.order,
                                                       k, w.boxes, class_aware ? w.ids : nullptr);
@@ -596,6 +589,67 @@ int mxd_nms(const DLTensor* boxes, const DLTensor* scores, const DLTensor* ids, 
   a.order = w.order; a.S = 1; a.stride = k; a.n_max = k; a.thr = iou_thr; a.delta = delta;
   a.max_out = max_out; a.mask = w.mask;
   // keep tensor may be shorter than k: resolve writes at most keep_stride rows
+  a.keep = dptr<int>(keep); a.keep_stride = cap; a.keep_cnt = dptr<int>(num_keep);
+  return launch_nms_sorted(a, st);
+}
+
+size_t mxd_nms_batched_workspace_bytes(int num_segments, int max_seg_len, int topk) {
+  if (num_segments < 0 || max_seg_len < 0) return 0;
+  return carve(nullptr, num_segments, eff_k(max_seg_len, topk), max_seg_len).bytes;
+}
+
+int mxd_nms_batched(const DLTensor* boxes, const DLTensor* scores, const DLTensor* ids, const DLTensor* seg_offsets,
+                    int max_seg_len, DLTensor* keep, DLTensor* num_keep, float iou_thr, float delta, int topk,
+                    float valid_thresh, int force_suppress, int max_out, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  int dev = -1, rc;
+  if ((rc = check_tensor(boxes, "boxes", F32, 2, 2, &dev))) return rc;
+  MXD_REQUIRE(boxes->shape[1] == 4, MXD_EINVAL, "boxes must be (n,4)");
+  const long long n = boxes->shape[0];
+  if ((rc = check_tensor(scores, "scores", F32, 1, 1, &dev))) return rc;
+  MXD_REQUIRE(scores->shape[0] == n, MXD_EINVAL, "scores must be (n)");
+  if (ids) {
+    if ((rc = check_tensor(ids, "ids", I32, 1, 1, &dev))) return rc;
+    MXD_REQUIRE(ids->shape[0] == n, MXD_EINVAL, "ids must be (n)");
+  }
+  if ((rc = check_tensor(seg_offsets, "seg_offsets", I32, 1, 1, &dev))) return rc;
+  MXD_REQUIRE(seg_offsets->shape[0] >= 1, MXD_EINVAL, "seg_offsets must be (S+1)");
+  const int S = (int)seg_offsets->shape[0] - 1;
+  if ((rc = check_tensor(keep, "keep", I32, 2, 2, &dev))) return rc;
+  if ((rc = check_tensor(num_keep, "num_keep", I32, 1, 1, &dev))) return rc;
+  MXD_REQUIRE(keep->shape[0] == S && num_keep->shape[0] == S, MXD_EINVAL, "keep / num_keep must be (S=%d, cap) / (S)", S);
+  MXD_REQUIRE(max_seg_len >= 0 && max_seg_len <= n, MXD_EINVAL, "max_seg_len %d not in [0, n]", max_seg_len);
+  MXD_REQUIRE(n == 0 || ((uintptr_t)dptr<float>(boxes) & 15) == 0, MXD_EINVAL, "boxes must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const int cap = (int)keep->shape[1];
+  if (S == 0) return MXD_OK;
+  const int k = eff_k(max_seg_len, topk);
+  if (k == 0 || cap == 0) {
+    MXD_CUDA_OK(cudaMemsetAsync(dptr<int>(num_keep), 0, sizeof(int) * (size_t)S, st));
+    if (cap) MXD_CUDA_OK(cudaMemsetAsync(dptr<int>(keep), 0xff, sizeof(int) * (size_t)S * cap, st));
+    return MXD_OK;
+  }
+  NmsWs w = carve(workspace, S, k, max_seg_len);
+  MXD_REQUIRE(workspace && workspace_bytes >= w.bytes, MXD_EWORKSPACE, "workspace %zu < %zu bytes", workspace_bytes,
+              w.bytes);
+  MXD_REQUIRE(((uintptr_t)workspace & 255) == 0, MXD_EINVAL, "workspace must be 256-byte aligned");
+  TopkParams p = {};
+  p.num_levels = 1; p.batch = S;
+  p.scores[0] = dptr<float>(scores); p.seg_stride[0] = 0; p.elem_stride = 1;
+  p.n[0] = max_seg_len; p.k[0] = k; p.kmax = k;
+  p.seg_off = dptr<int>(seg_offsets);
+  p.valid_thresh = valid_thresh;
+  p.out_idx = w.order; p.out_val = nullptr; p.out_cnt = w.cnt;
+  if ((rc = launch_topk(p, st, w.sortws, w.sort_bytes))) return rc;
+  const bool class_aware = ids && !force_suppress;
+  nms_gather_seg_kernel<<<dim3((k + 255) / 256, S), 256, 0, st>>>(dptr<float>(boxes), class_aware ? dptr<int>(ids) : nullptr,
+                                                                  dptr<int>(seg_offsets), w.order, k, w.boxes,
+                                                                  class_aware ? w.ids : nullptr);
+  MXD_POST_LAUNCH("nms_gather_seg");
+  NmsSortedArgs a = {};
+  a.boxes = w.boxes; a.valid = nullptr; a.ids = class_aware ? w.ids : nullptr; a.counts = w.cnt;
+  a.order = w.order; a.S = S; a.stride = k; a.n_max = k; a.thr = iou_thr; a.delta = delta;
+  a.max_out = max_out; a.mask = w.mask;
   a.keep = dptr<int>(keep); a.keep_stride = cap; a.keep_cnt = dptr<int>(num_keep);
   return launch_nms_sorted(a, st);
 }
@@ -688,7 +742,7 @@ int mxd_det_bboxes(const DLTensor* boxes, const DLTensor* deltas, const DLTensor
   return MXD_OK;
 }
 
-size_t mxd_box_nms_workspace_bytes(int batch, int n, int topk) { return carve(nullptr, batch, eff_k(n, topk)).bytes; }
+size_t mxd_box_nms_workspace_bytes(int batch, int n, int topk) { return carve(nullptr, batch, eff_k(n, topk), n).bytes; }
 
 int mxd_box_nms(const DLTensor* data, DLTensor* out, DLTensor* index, float overlap_thresh, float valid_thresh,
                 int topk, int coord_start, int score_index, int id_index, int force_suppress, int in_format,
@@ -709,9 +763,7 @@ int mxd_box_nms(const DLTensor* data, DLTensor* out, DLTensor* index, float over
   }
   if (B == 0 || N == 0) return MXD_OK;
   const int k = eff_k(N, topk);
-  MXD_REQUIRE(k <= MXD_SORT_CAP, MXD_ENOTSUP,
-              "box_nms over %d rows exceeds the in-CTA sort capacity %d (pass topk)", k, MXD_SORT_CAP);
-  NmsWs w = carve(workspace, B, k);
+  NmsWs w = carve(workspace, B, k, N);
   MXD_REQUIRE(workspace && workspace_bytes >= w.bytes, MXD_EWORKSPACE, "workspace %zu < %zu bytes",
               workspace_bytes, w.bytes);
   cudaStream_t st = as_stream(stream);
@@ -721,7 +773,7 @@ int mxd_box_nms(const DLTensor* data, DLTensor* out, DLTensor* index, float over
   p.n[0] = (int)N; p.k[0] = k; p.kmax = k;
   p.valid_thresh = valid_thresh;
   p.out_idx = w.order; p.out_cnt = w.cnt;
-  if ((rc = launch_topk(p, st))) return rc;
+  if ((rc = launch_topk(p, st, w.sortws, w.sort_bytes))) return rc;
   const bool class_aware = id_index >= 0 && !force_suppress;
   dim3 g1((k + 255) / 256, B);
   boxnms_gather_kernel<<<g1, 256, 0, st>>>(dptr<float>(data), w.order, (int)N, K, k, coord_start,

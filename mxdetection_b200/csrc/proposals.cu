@@ -98,11 +98,12 @@ __global__ void __launch_bounds__(kCollectThreads, 1) rpn_collect_kernel(Collect
 
 struct RpnWs {
   int* idx; float* vals; float4* boxes; uint8_t* valid; int* cnt; u64* mask; int* keep; int* keep_cnt;
+  void* sortws; size_t sort_bytes;      // chunk-sort scratch when nms_pre exceeds MXD_SORT_CAP
   int kmax, keep_stride;
   size_t bytes;
 };
 
-static int rpn_dims(const mxd_rpn_config* c, int* kmax, int* keep_stride) {
+static int rpn_dims(const mxd_rpn_config* c, int* kmax, int* keep_stride, long long* nmax = nullptr) {
   MXD_REQUIRE(c != nullptr, MXD_EINVAL, "null config");
   MXD_REQUIRE(c->num_levels >= 1 && c->num_levels <= MXD_MAX_LEVELS, MXD_EINVAL, "num_levels %d not in [1,%d]",
               c->num_levels, MXD_MAX_LEVELS);
@@ -115,8 +116,8 @@ static int rpn_dims(const mxd_rpn_config* c, int* kmax, int* keep_stride) {
     const long long n = (long long)c->feat_h[l] * c->feat_w[l] * c->num_base;
     MXD_REQUIRE(n < (1ll << 31), MXD_ENOTSUP, "level too large");
     const long long k = (c->nms_pre > 0 && c->nms_pre < n) ? c->nms_pre : n;
-    MXD_REQUIRE(k <= MXD_SORT_CAP, MXD_ENOTSUP, "per-level candidates %lld exceed %d (set nms_pre)", k, MXD_SORT_CAP);
     km = k > km ? (int)k : km;
+    if (nmax && n > *nmax) *nmax = n;
   }
   if (km < 1) km = 1;
   const int ks = (c->nms_post > 0 && c->nms_post < km) ? c->nms_post : km;
@@ -129,7 +130,7 @@ static int rpn_dims(const mxd_rpn_config* c, int* kmax, int* keep_stride) {
   return MXD_OK;
 }
 
-static RpnWs carve_rpn(void* base, int S, int kmax, int ks) {
+static RpnWs carve_rpn(void* base, int S, int kmax, int ks, long long nmax) {
   RpnWs w;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (char*)base + o; };
@@ -141,6 +142,8 @@ static RpnWs carve_rpn(void* base, int S, int kmax, int ks) {
   w.mask = (u64*)take(sizeof(u64) * nms_mask_words(S, kmax));
   w.keep = (int*)take(sizeof(int) * (size_t)S * ks);
   w.keep_cnt = (int*)take(sizeof(int) * (size_t)S);
+  w.sort_bytes = topk_long_workspace_bytes(S, nmax, kmax);
+  w.sortws = take(w.sort_bytes);
   w.kmax = kmax; w.keep_stride = ks;
   w.bytes = off;
   return w;
@@ -154,8 +157,9 @@ extern "C" {
 
 size_t mxd_rpn_proposals_workspace_bytes(const mxd_rpn_config* cfg, int batch) {
   int km, ks;
-  if (rpn_dims(cfg, &km, &ks) != MXD_OK || batch < 0) return 0;
-  return carve_rpn(nullptr, batch * cfg->num_levels, km, ks).bytes;
+  long long nmax = 0;
+  if (rpn_dims(cfg, &km, &ks, &nmax) != MXD_OK || batch < 0) return 0;
+  return carve_rpn(nullptr, batch * cfg->num_levels, km, ks, nmax).bytes;
 }
 
 int mxd_rpn_proposals_dims(const mxd_rpn_config* cfg, int* kmax, int* keep_stride) {
@@ -167,7 +171,8 @@ int mxd_rpn_proposals(const DLTensor* const* scores, const DLTensor* const* delt
                       const mxd_rpn_config* cfg, DLTensor* proposals, DLTensor* num_valid, void* workspace,
                       size_t workspace_bytes, void* stream) {
   int dev = -1, rc, km, ks;
-  if ((rc = rpn_dims(cfg, &km, &ks))) return rc;
+  long long nmax = 0;
+  if ((rc = rpn_dims(cfg, &km, &ks, &nmax))) return rc;
   MXD_REQUIRE(scores && deltas, MXD_EINVAL, "null level tables");
   const int L = cfg->num_levels;
   int B = -1;
@@ -202,7 +207,7 @@ int mxd_rpn_proposals(const DLTensor* const* scores, const DLTensor* const* delt
   MXD_REQUIRE(cfg->wh_ratio_clip > 0, MXD_EINVAL, "wh_ratio_clip must be > 0");
   if (B == 0) return MXD_OK;
   const int S = B * L;
-  RpnWs w = carve_rpn(workspace, S, km, ks);
+  RpnWs w = carve_rpn(workspace, S, km, ks, nmax);
   MXD_REQUIRE(workspace && workspace_bytes >= w.bytes, MXD_EWORKSPACE, "workspace %zu < %zu bytes", workspace_bytes,
               w.bytes);
   MXD_REQUIRE(((uintptr_t)workspace & 255) == 0, MXD_EINVAL, "workspace must be 256-byte aligned");
@@ -217,7 +222,7 @@ int mxd_rpn_proposals(const DLTensor* const* scores, const DLTensor* const* delt
   for (int j = 0; j < 4; ++j) { p.means[j] = cfg->means[j]; p.stds[j] = cfg->stds[j]; }
   p.max_ratio = (float)fabs(log(cfg->wh_ratio_clip));
   p.min_size = cfg->min_bbox_size;
-  if ((rc = launch_topk(p, st))) return rc;
+  if ((rc = launch_topk(p, st, w.sortws, w.sort_bytes))) return rc;
 
   NmsSortedArgs a = {};
   a.boxes = w.boxes; a.valid = w.valid; a.ids = nullptr; a.counts = w.cnt; a.order = nullptr;
@@ -242,9 +247,10 @@ int mxd_rpn_proposals(const DLTensor* const* scores, const DLTensor* const* delt
 int mxd_rpn_proposals_stages(const mxd_rpn_config* cfg, int batch, const void* workspace, size_t workspace_bytes,
                              DLTensor* idx, DLTensor* boxes, DLTensor* keep, DLTensor* counts, void* stream) {
   int dev = -1, rc, km, ks;
-  if ((rc = rpn_dims(cfg, &km, &ks))) return rc;
+  long long nmax = 0;
+  if ((rc = rpn_dims(cfg, &km, &ks, &nmax))) return rc;
   const int S = batch * cfg->num_levels;
-  RpnWs w = carve_rpn(const_cast<void*>(workspace), S, km, ks);
+  RpnWs w = carve_rpn(const_cast<void*>(workspace), S, km, ks, nmax);
   MXD_REQUIRE(workspace && workspace_bytes >= w.bytes, MXD_EWORKSPACE, "workspace too small");
   if ((rc = check_tensor(idx, "idx", I32, 3, 3, &dev))) return rc;
   if ((rc = check_tensor(boxes, "boxes", F32, 4, 4, &dev))) return rc;

@@ -19,6 +19,8 @@
 // through distributed shared memory, every CTA derives the same bound L, compacts its own share, and the
 // survivors are funnelled into CTA 0 for the final sort (one CTA scanning 650 KB twice measured 138 us).
 #include <cooperative_groups.h>
+#include <stdlib.h>
+#include <algorithm>
 #include "internal.h"
 
 namespace cg = cooperative_groups;
@@ -184,6 +186,54 @@ __device__ u64 radix_select_kth(const float* __restrict__ sc, int estride, int n
   return prefix;  // select keys >= prefix (low unprocessed bits are zero)
 }
 
+// Geometry of segment s: uniform (b, l) segments of per-level arrays, or ragged segments of one array (seg_off).
+struct SegGeom { int b, l, n, k; const float* sc; };
+__device__ __forceinline__ SegGeom seg_geom(const TopkParams& p, int s) {
+  SegGeom g;
+  if (p.seg_off) {
+    const int lo = p.seg_off[s], hi = p.seg_off[s + 1];
+    g.b = s; g.l = 0; g.n = max(hi - lo, 0); g.k = min(p.k[0], g.n); g.sc = p.scores[0] + lo;
+  } else {
+    g.b = s / p.num_levels; g.l = s - g.b * p.num_levels;
+    g.n = p.n[g.l]; g.k = p.k[g.l]; g.sc = p.scores[g.l] + (size_t)g.b * p.seg_stride[g.l];
+  }
+  return g;
+}
+
+// One output row j of segment s (key 0 = padding): index, value and - when enabled - the regenerated anchor decoded
+// with the row's deltas (Spec C + Spec F) and the min-size flag.
+__device__ __forceinline__ void emit_row(const TopkParams& p, int s, const SegGeom& g, int j, u64 key) {
+  const bool ok = key != 0;
+  const int b = g.b, l = g.l, n = g.n;
+  const int i = ok ? n - 1 - (int)(uint32_t)key : -1;
+  const float* __restrict__ sc = g.sc;
+  p.out_idx[(size_t)s * p.kmax + j] = i;
+  if (p.out_val) p.out_val[(size_t)s * p.kmax + j] = ok ? sc[(size_t)i * p.elem_stride] : 0.0f;
+  if (p.out_boxes) {
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint8_t v = 0;
+    if (ok) {
+      const float hmax = (float)(p.img_shapes[2 * b] - 1), wmax = (float)(p.img_shapes[2 * b + 1] - 1);
+      const int A = p.num_base;
+      const int a = i % A, cell = i / A;
+      const int x = cell % p.feat_w[l], y = cell / p.feat_w[l];
+      const float sx = __fmul_rn((float)x, p.stride[l]), sy = __fmul_rn((float)y, p.stride[l]);
+      float4 anc;
+      anc.x = __fadd_rn(p.base[l][a][0], sx); anc.y = __fadd_rn(p.base[l][a][1], sy);
+      anc.z = __fadd_rn(p.base[l][a][2], sx); anc.w = __fadd_rn(p.base[l][a][3], sy);
+      const float4 dl = reinterpret_cast<const float4*>(p.deltas[l])[(size_t)b * n + i];
+      box = decode_box(anc, dl, p.means, p.stds, p.max_ratio, hmax, wmax, true);
+      v = 1;
+      if (p.min_size > 0.f) {
+        const float w = __fadd_rn(__fsub_rn(box.z, box.x), 1.0f), h = __fadd_rn(__fsub_rn(box.w, box.y), 1.0f);
+        v = (w >= p.min_size && h >= p.min_size) ? 1 : 0;
+      }
+    }
+    p.out_boxes[(size_t)s * p.kmax + j] = box;
+    p.out_valid[(size_t)s * p.kmax + j] = v;
+  }
+}
+
 template <bool CLUSTER>
 __global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __grid_constant__ TopkParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -196,11 +246,11 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __g
   const int rank = CLUSTER ? (int)cg::this_cluster().block_rank() : 0;
   const int csz = CLUSTER ? (int)cg::this_cluster().num_blocks() : 1;     // 8 or 4 CTAs
   const int s = CLUSTER ? blockIdx.x / csz : blockIdx.x;
-  const int b = s / p.num_levels, l = s - b * p.num_levels;
-  const int n = p.n[l], k = p.k[l];
+  const SegGeom sg = seg_geom(p, s);
+  const int n = sg.n, k = sg.k;
   const int es = p.elem_stride;
   const float vt = p.valid_thresh;
-  const float* __restrict__ sc = p.scores[l] + (size_t)b * p.seg_stride[l];
+  const float* __restrict__ sc = sg.sc;
   const int tid = threadIdx.x;
   int count;
 
@@ -422,41 +472,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __g
   bitonic_sort_desc(keys, P);
 
   // ---- emit -------------------------------------------------------------------
-  int* oi = p.out_idx + (size_t)s * p.kmax;
-  float hmax = 0.f, wmax = 0.f;
-  if (p.out_boxes) {
-    hmax = (float)(p.img_shapes[2 * b] - 1);
-    wmax = (float)(p.img_shapes[2 * b + 1] - 1);
-  }
-  for (int j = tid; j < p.kmax; j += kTopkThreads) {
-    const u64 key = (j < k && j < P) ? keys[j] : 0ull;
-    const bool ok = key != 0;
-    const int i = ok ? n - 1 - (int)(uint32_t)key : -1;
-    oi[j] = i;
-    if (p.out_val) p.out_val[(size_t)s * p.kmax + j] = ok ? sc[(size_t)i * es] : 0.0f;
-    if (p.out_boxes) {
-      float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-      uint8_t v = 0;
-      if (ok) {
-        const int A = p.num_base;
-        const int a = i % A, cell = i / A;
-        const int x = cell % p.feat_w[l], y = cell / p.feat_w[l];
-        const float sx = __fmul_rn((float)x, p.stride[l]), sy = __fmul_rn((float)y, p.stride[l]);
-        float4 anc;
-        anc.x = __fadd_rn(p.base[l][a][0], sx); anc.y = __fadd_rn(p.base[l][a][1], sy);
-        anc.z = __fadd_rn(p.base[l][a][2], sx); anc.w = __fadd_rn(p.base[l][a][3], sy);
-        const float4 dl = reinterpret_cast<const float4*>(p.deltas[l])[(size_t)b * n + i];
-        box = decode_box(anc, dl, p.means, p.stds, p.max_ratio, hmax, wmax, true);
-        v = 1;
-        if (p.min_size > 0.f) {
-          const float w = __fadd_rn(__fsub_rn(box.z, box.x), 1.0f), h = __fadd_rn(__fsub_rn(box.w, box.y), 1.0f);
-          v = (w >= p.min_size && h >= p.min_size) ? 1 : 0;
-        }
-      }
-      p.out_boxes[(size_t)s * p.kmax + j] = box;
-      p.out_valid[(size_t)s * p.kmax + j] = v;
-    }
-  }
+  for (int j = tid; j < p.kmax; j += kTopkThreads) emit_row(p, s, sg, j, (j < k && j < P) ? keys[j] : 0ull);
   if (p.out_cnt && tid == 0) {
     // real rows = position of the first zero key (keys are sorted, zeros last)
     int lo = 0, hi = min(k, P);
@@ -468,12 +484,99 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_segment_kernel(const __g
   }
 }
 
-int launch_topk(const TopkParams& p, cudaStream_t st) {
+// ---- long path: k above the in-CTA sort capacity ------------------------------------------------------------
+// (1) every chunk of kCap keys is sorted by one CTA (bitonic, shared memory) into the workspace; (2) the global rank
+// of a key is its position in its own chunk plus, for every other chunk, the number of larger keys there (a binary
+// search: keys are unique, so the ranks are a permutation) - rows with rank < k are emitted straight to out[rank].
+// O(n * chunks * log) work instead of a global radix sort; this path serves box_nms / MultiProposal calls over more
+// than 8192 rows, which the detector configs of the lineage do not reach on the hot path.
+__global__ void __launch_bounds__(kTopkThreads, 1) topk_chunk_sort_kernel(const __grid_constant__ TopkParams p, u64* ws,
+                                                                           int nchunks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64* keys = reinterpret_cast<u64*>(smem_raw);
+  const int c = blockIdx.x, s = blockIdx.y;
+  const SegGeom sg = seg_geom(p, s);
+  const int n = sg.n;
+  const float* __restrict__ sc = sg.sc;
+  for (int j = threadIdx.x; j < kCap; j += kTopkThreads) {
+    const long long i = (long long)c * kCap + j;
+    keys[j] = i < n ? make_key(sc[(size_t)i * p.elem_stride], (int)i, n, p.valid_thresh) : 0ull;
+  }
+  __syncthreads();
+  bitonic_sort_desc(keys, kCap);
+  u64* o = ws + ((size_t)s * nchunks + c) * kCap;
+  for (int j = threadIdx.x; j < kCap; j += kTopkThreads) o[j] = keys[j];
+}
+
+__global__ void __launch_bounds__(kTopkThreads, 1) topk_merge_rank_kernel(const __grid_constant__ TopkParams p,
+                                                                           const u64* __restrict__ ws, int nchunks) {
+  __shared__ int s_valid;
+  const int c = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
+  const SegGeom sg = seg_geom(p, s);
+  const int k = sg.k;
+  const u64* seg = ws + (size_t)s * nchunks * kCap;
+  if (tid == 0) s_valid = 0;
+  __syncthreads();
+  // valid rows of the segment: non-zero keys (sorted descending, zeros last) of every chunk
+  for (int q = tid; q < nchunks; q += kTopkThreads) {
+    const u64* ch = seg + (size_t)q * kCap;
+    int lo = 0, hi = kCap;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ch[mid] != 0) lo = mid + 1; else hi = mid; }
+    if (lo) atomicAdd(&s_valid, lo);
+  }
+  __syncthreads();
+  const int valid = min(s_valid, k);
+  if (c == 0) {
+    for (int j = valid + tid; j < p.kmax; j += kTopkThreads) emit_row(p, s, sg, j, 0ull);
+    if (p.out_cnt && tid == 0) p.out_cnt[s] = valid;
+  }
+  const u64* mine = seg + (size_t)c * kCap;
+  for (int j = tid; j < kCap; j += kTopkThreads) {
+    const u64 key = mine[j];
+    if (key == 0) break;                          // zeros are last
+    int rank = j;
+    for (int q = 0; q < nchunks && rank < k; ++q) {
+      if (q == c) continue;
+      const u64* ch = seg + (size_t)q * kCap;
+      int lo = 0, hi = kCap;                       // number of keys of chunk q larger than mine
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (ch[mid] > key) lo = mid + 1; else hi = mid; }
+      rank += lo;
+    }
+    if (rank < k) emit_row(p, s, sg, rank, key);
+  }
+}
+
+size_t topk_long_workspace_bytes(int S, long long n_max, int k_max) {
+  if (k_max <= kCap && getenv("MXD_TOPK_FORCE_LONG") == nullptr) return 0;
+  const long long nchunks = (n_max + kCap - 1) / kCap;
+  return align_up(sizeof(u64) * (size_t)S * (size_t)nchunks * kCap, 256);
+}
+
+int launch_topk(const TopkParams& p, cudaStream_t st, void* long_ws, size_t long_ws_bytes) {
   const int S = p.batch * p.num_levels;
   if (S == 0) return MXD_OK;
+  int kbig_all = 0;
+  long long nbig_all = 0;
   for (int l = 0; l < p.num_levels; ++l) {
-    MXD_REQUIRE(p.k[l] <= kCap, MXD_ENOTSUP, "top-k of %d rows exceeds the in-CTA sort capacity %d", p.k[l], kCap);
     MXD_REQUIRE(p.k[l] <= p.kmax && p.n[l] >= 0, MXD_EINVAL, "bad top-k geometry");
+    kbig_all = std::max(kbig_all, p.k[l]);
+    nbig_all = std::max<long long>(nbig_all, p.n[l]);
+  }
+  static unsigned long long seen_long = 0;
+  if (kbig_all > kCap || getenv("MXD_TOPK_FORCE_LONG") != nullptr) {        // (tests force the long path on short inputs)
+    const int nchunks = (int)((nbig_all + kCap - 1) / kCap);
+    const size_t need = align_up(sizeof(u64) * (size_t)S * (size_t)nchunks * kCap, 256);
+    MXD_REQUIRE(long_ws != nullptr && long_ws_bytes >= need, MXD_EWORKSPACE,
+                "top-k of %d rows needs a %zu-byte sort workspace (got %zu)", kbig_all, need, long_ws_bytes);
+    MXD_REQUIRE(S <= 65535 && nchunks >= 1, MXD_ENOTSUP, "too many top-k segments");
+    const int smem = kCap * (int)sizeof(u64);
+    if (first_use_on_device(&seen_long))
+      MXD_CUDA_OK(cudaFuncSetAttribute(topk_chunk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    topk_chunk_sort_kernel<<<dim3(nchunks, S), kTopkThreads, smem, st>>>(p, static_cast<u64*>(long_ws), nchunks);
+    MXD_POST_LAUNCH("topk_chunk_sort");
+    topk_merge_rank_kernel<<<dim3(nchunks, S), kTopkThreads, 0, st>>>(p, static_cast<const u64*>(long_ws), nchunks);
+    MXD_POST_LAUNCH("topk_merge_rank");
+    return MXD_OK;
   }
   bool big = false;
   for (int l = 0; l < p.num_levels; ++l) big = big || p.n[l] > kCap;
@@ -513,10 +616,13 @@ using namespace mxd;
 
 extern "C" {
 
-size_t mxd_topk_stable_workspace_bytes(int, int, int) { return 0; }
+size_t mxd_topk_stable_workspace_bytes(int segments, int n, int topk) {
+  const int k = (topk > 0 && topk < n) ? topk : n;
+  return topk_long_workspace_bytes(segments, n, k);
+}
 
-int mxd_topk_stable(const DLTensor* scores, DLTensor* idx, DLTensor* vals, int topk, void* /*workspace*/,
-                    size_t /*workspace_bytes*/, void* stream) {
+int mxd_topk_stable(const DLTensor* scores, DLTensor* idx, DLTensor* vals, int topk, void* workspace,
+                    size_t workspace_bytes, void* stream) {
   int dev = -1, rc;
   if ((rc = check_tensor(scores, "scores", F32, 1, 2, &dev))) return rc;
   const int S = scores->ndim == 2 ? (int)scores->shape[0] : 1;
@@ -537,7 +643,7 @@ int mxd_topk_stable(const DLTensor* scores, DLTensor* idx, DLTensor* vals, int t
   p.valid_thresh = -INFINITY;
   p.out_idx = dptr<int>(idx);
   p.out_val = vals ? dptr<float>(vals) : nullptr;
-  return launch_topk(p, as_stream(stream));
+  return launch_topk(p, as_stream(stream), workspace, workspace_bytes);
 }
 
 }  // extern "C"

@@ -22,7 +22,11 @@ def topk_stable(scores, k):
     shape = tuple(scores.shape[:-1]) + (kk,)
     idx = torch.empty(shape, dtype=torch.int32, device=scores.device)
     vals = torch.empty(shape, dtype=torch.float32, device=scores.device)
-    L.call("mxd_topk_stable", L.dl(scores), L.dl(idx), L.dl(vals), int(k), None, 0, L.current_stream(scores.device))
+    segs = int(scores.numel() // max(n, 1))
+    nbytes = L.lib.mxd_topk_stable_workspace_bytes(segs, int(n), int(k))     # > 0 only above MXD_SORT_CAP rows
+    ws = L.workspace(nbytes, scores.device, "topk") if nbytes else None
+    L.call("mxd_topk_stable", L.dl(scores), L.dl(idx), L.dl(vals), int(k), ws.data_ptr() if nbytes else None,
+           ws.numel() if nbytes else 0, L.current_stream(scores.device))
     return idx, vals
 
 
@@ -34,13 +38,32 @@ def nms_indices(boxes, scores, iou_thr, delta=0.0, topk=-1, valid_thresh=-math.i
     n = boxes.shape[0]
     k = topk if 0 < topk < n else n
     cap = min(k, max_out) if max_out > 0 else k
-    keep = torch.full((max(cap, 0),), -1, dtype=torch.int32, device=boxes.device)
-    num = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
+    keep = torch.empty((max(cap, 0),), dtype=torch.int32, device=boxes.device)      # the library pads with -1
+    num = torch.empty((1,), dtype=torch.int32, device=boxes.device)
     nbytes = L.lib.mxd_nms_workspace_bytes(int(n), int(topk))
     ws = L.workspace(nbytes, boxes.device, "nms")
     L.call("mxd_nms", L.dl(boxes), L.dl(scores), L.dl(ids), L.dl(keep), L.dl(num), float(iou_thr), float(delta),
            int(topk), float(valid_thresh), 1 if force_suppress else 0, int(max_out), ws.data_ptr(), ws.numel(),
            L.current_stream(boxes.device))
+    return keep, num
+
+
+def nms_batched(boxes, scores, seg_offsets, max_seg_len, iou_thr, delta=0.0, topk=-1, valid_thresh=-math.inf, ids=None,
+                force_suppress=True, max_out=-1):
+    """NMS over ragged segments of one box array (segment s = rows seg_offsets[s] .. seg_offsets[s+1], int32 on the
+    device; max_seg_len a host upper bound).  Returns (keep (S,cap) int32 GLOBAL row indices, -1 padded; num_keep (S))."""
+    L.require_cuda(boxes, scores, seg_offsets, ids)
+    boxes = boxes.contiguous(); scores = scores.contiguous(); seg_offsets = seg_offsets.contiguous()
+    S = seg_offsets.shape[0] - 1
+    k = topk if 0 < topk < max_seg_len else max_seg_len
+    cap = min(k, max_out) if max_out > 0 else k
+    keep = torch.empty((S, max(cap, 0)), dtype=torch.int32, device=boxes.device)
+    num = torch.empty((S,), dtype=torch.int32, device=boxes.device)
+    nbytes = L.lib.mxd_nms_batched_workspace_bytes(int(S), int(max_seg_len), int(topk))
+    ws = L.workspace(nbytes, boxes.device, "nms_batched")
+    L.call("mxd_nms_batched", L.dl(boxes), L.dl(scores), L.dl(ids), L.dl(seg_offsets), int(max_seg_len), L.dl(keep),
+           L.dl(num), float(iou_thr), float(delta), int(topk), float(valid_thresh), 1 if force_suppress else 0,
+           int(max_out), ws.data_ptr(), ws.numel(), L.current_stream(boxes.device))
     return keep, num
 
 

@@ -422,6 +422,76 @@ def test_nms_vs_oracle_bit_exact(n, delta):
     assert int(num.item()) == len(ref) and np.array_equal(N(keep)[: len(ref)], ref)
 
 
+@pytest.mark.parametrize("n,k", [(9000, 9000), (20000, 12000), (70001, 70001), (300, 300), (16384, 8193)])
+def test_topk_stable_beyond_the_in_cta_sort(n, k):
+    """k above MXD_SORT_CAP (8192): the chunk-sort + rank-merge path (also forced on a short input)."""
+    from mxdetection_b200.ops import topk_stable
+    rng = np.random.default_rng(n)
+    s = (np.round(rng.uniform(0, 1, (2, n)) * 4096) / 4096).astype(F)     # ties
+    s[1, ::3] = 0.125
+    if k <= 8192:
+        os.environ["MXD_TOPK_FORCE_LONG"] = "1"      # read by the workspace query and by the launcher
+    try:
+        idx, vals = topk_stable(T(s), k)
+    finally:
+        os.environ.pop("MXD_TOPK_FORCE_LONG", None)
+    for r in range(2):
+        ref = oracle.topk_stable(s[r], k)
+        assert np.array_equal(N(idx)[r], ref) and np.array_equal(N(vals)[r], s[r][ref])
+
+
+@pytest.mark.parametrize("n,force", [(9000, False), (12000, False), (20000, False), (700, True), (64, True)])
+def test_nms_long_segments_beyond_8192_rows(n, force):
+    """mx.nd.contrib.box_nms has no row cap: above 8192 rows the sort takes the chunked path, and above ~9400 rows the
+    greedy resolve reads the row-major mask from L2 (forced here for short inputs too)."""
+    from mxdetection_b200.ops import nms_indices, box_nms
+    rng = np.random.default_rng(n)
+    span = 30 * math.sqrt(n) + 20
+    xy = rng.uniform(0, span, (n, 2)); wh = rng.uniform(4, 100, (n, 2))
+    boxes = np.concatenate([xy, xy + wh], 1).astype(F)
+    scores = (np.round(rng.uniform(0, 1, n) * 512) / 512).astype(F)
+    if force:
+        os.environ["MXD_NMS_FORCE_GLOBAL"] = "1"
+    try:
+        ref = oracle.nms(boxes, scores, 0.6, delta=0.0)
+        keep, num = nms_indices(T(boxes), T(scores), 0.6, delta=0.0)
+        assert int(num.item()) == len(ref) and np.array_equal(N(keep)[: len(ref)], ref)
+        ref2 = oracle.nms(boxes, scores, 0.6, delta=0.0, max_out=37, valid_thresh=0.3)
+        keep, num = nms_indices(T(boxes), T(scores), 0.6, delta=0.0, max_out=37, valid_thresh=0.3)
+        assert int(num.item()) == len(ref2) and np.array_equal(N(keep)[: len(ref2)], ref2)
+        if n <= 12000:
+            data = np.concatenate([rng.integers(0, 3, (n, 1)).astype(F), scores[:, None], boxes], 1)[None]
+            out = N(box_nms(T(data), overlap_thresh=0.6, valid_thresh=0.0, id_index=0))
+            assert np.array_equal(out, oracle.box_nms_mx(data, overlap_thresh=0.6, valid_thresh=0.0, id_index=0))
+    finally:
+        os.environ.pop("MXD_NMS_FORCE_GLOBAL", None)
+
+
+def test_nms_batched_ragged_segments():
+    """mxd_nms_batched: segments of different lengths (empty, 1, > 64, > 8192 rows) of one box array; keep lists are
+    global row indices and equal the per-segment oracle."""
+    from mxdetection_b200.ops import nms_batched
+    rng = np.random.default_rng(12)
+    lens = [0, 1, 700, 65, 0, 2000, 9001, 3]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    n = int(off[-1])
+    xy = rng.uniform(0, 900, (n, 2)); wh = rng.uniform(4, 120, (n, 2))
+    boxes = np.concatenate([xy, xy + wh], 1).astype(F)
+    scores = (np.round(rng.uniform(0, 1, n) * 256) / 256).astype(F)
+    ids = rng.integers(0, 4, n).astype(np.int32)
+    for kw in (dict(), dict(topk=500, max_out=100), dict(ids=ids, force_suppress=False, valid_thresh=0.25)):
+        tk = {k: (T(v) if k == "ids" else v) for k, v in kw.items()}
+        keep, num = nms_batched(T(boxes), T(scores), T(off), max(lens), 0.5, delta=1.0, **tk)
+        keep, num = N(keep), N(num)
+        for s_, (a, b) in enumerate(zip(off[:-1], off[1:])):
+            okw = dict(kw)
+            if "ids" in okw:
+                okw["ids"] = ids[a:b]
+            ref = oracle.nms(boxes[a:b], scores[a:b], 0.5, delta=1.0, **okw) + a
+            assert num[s_] == len(ref) and np.array_equal(keep[s_, : len(ref)], ref), (kw, s_)
+            assert np.all(keep[s_, len(ref):] == -1)
+
+
 def test_nms_dependency_chains():
     """Worst case of the scan kernel's fixed point: every box overlaps only its neighbours, so whether box i survives
     depends on box i-1, ... all the way down (64 rounds per block), across block boundaries, with ties."""
@@ -704,8 +774,9 @@ def test_rpn_proposals_stock_training_config_2000x5_levels():
     assert np.array_equal(nv, rn) and np.array_equal(props, ro) and np.all(nv == 2000)
 
 
+# (1, 50, 68, 12000, 2000): the mx-rcnn TRAINING proposal config (rpn_pre_nms_top_n 12000 > the in-CTA sort capacity)
 @pytest.mark.parametrize("N_,H,W,pre,post,scales", [(2, 38, 50, 6000, 300, (4, 8, 16, 32)), (1, 25, 34, 1000, 50, (8, 16, 32)),
-                                                    (3, 7, 9, 200, 600, (2,))])
+                                                    (3, 7, 9, 200, 600, (2,)), (1, 50, 68, 12000, 2000, (4, 8, 16, 32))])
 def test_multi_proposal_mx_layout(N_, H, W, pre, post, scales):
     """mx.nd.contrib.MultiProposal (NCHW in, cyclically padded rois out) vs the oracle: identical rows."""
     from mxdetection_b200.models.rpn_heads import MultiProposal
