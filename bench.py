@@ -190,20 +190,33 @@ def touched_bytes(rois, levels, shapes, scales, nimg, channels, pooled, sr):
 
 
 # ------------------------------------------------------------------ reference arm --
-def cpu_reference_fpn(n_images, passes, first_image=0):
+def load_synthetic():
+    """mxdetection_b200/synthetic.py loaded BY PATH: the reference arm must not import the product package (that
+    would map libmxdet_sm100.so into the reference process)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_mxd_synthetic", os.path.join(ROOT, "mxdetection_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_reference_fpn(n_images, passes, first_image=0, keep=False):
     """Times the C port of the reference CPU path (oracle/cpu_ref.c: OpenMP-over-RoIs forward, serial
     backward - the parallelisation of mxnet 1.3's roi_align.cc) on `n_images` images of the workload."""
     from oracle import cref
-    from mxdetection_b200 import synthetic as syn
+    syn = load_synthetic()
     d = syn.cfg3(batch=n_images, first_image=first_image, with_features=True)
     lv = cref.map_roi_levels(d["rois"], 4)
     shapes = [f.shape for f in d["feats"]]
     times = []
+    out = grads = None
     for _ in range(passes):
         t0 = time.perf_counter()
-        cref.roi_align_forward(d["feats"], d["rois"], POOLED, d["scales"], 2, lv)
-        cref.roi_align_backward(d["grad_out"], d["rois"], shapes, POOLED, d["scales"], 2, lv)
+        out = cref.roi_align_forward(d["feats"], d["rois"], POOLED, d["scales"], 2, lv)
+        grads = cref.roi_align_backward(d["grad_out"], d["rois"], shapes, POOLED, d["scales"], 2, lv)
         times.append(time.perf_counter() - t0)
+    if keep:
+        return n_images * ROIS_PER_IMG, times, cref.num_threads(), (d, out, grads)
     return n_images * ROIS_PER_IMG, times, cref.num_threads()
 
 
@@ -211,6 +224,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the reference arm is ONE process that may use
+    # every host core, so the OpenMP runtime is told so before it starts (recorded in the line)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     rois, times, threads = cpu_reference_fpn(1, args.warmup + args.steps)
     times = times[args.warmup:]
     total = sum(times)
@@ -222,7 +238,8 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "host_cpus": os.cpu_count()}
+            "gpu_launches": 0, "host_cpus": os.cpu_count(), "omp_num_threads": os.environ.get("OMP_NUM_THREADS"),
+            "product_library_loaded": "mxdetection_b200" in sys.modules}
     print(json.dumps(line))
     return 0
 
@@ -258,6 +275,10 @@ def run_ours(args):
         finally:
             sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     K, Wm = args.steps, max(args.warmup, 3)
+    global IMGS_PER_GPU
+    if args.scaling == "strong":
+        assert 64 % world == 0, "strong scaling splits the 64 images of BASELINE config 5 evenly"
+        IMGS_PER_GPU = 64 // world
     first_image = rank * IMGS_PER_GPU
     peak_gbs, peak_src = measured_peaks()
 
@@ -321,7 +342,7 @@ def run_ours(args):
     alg_bwd = out_bytes + map_bytes                   # read grad_out + write every grad-map byte (req=write)
     dom = "roi_align_backward" if bwd_ms >= fwd_ms else "roi_align_forward"
     dom_ms = max(fwd_ms, bwd_ms); dom_bytes = alg_bwd if bwd_ms >= fwd_ms else alg_fwd
-    traffic = ncu_traffic("roi_align_tile_bwd_kernel" if bwd_ms >= fwd_ms else "roi_align_stream_fwd_kernel")
+    traffic = ncu_traffic("roi_align_tile_bwd_kernel" if bwd_ms >= fwd_ms else "roi_align_ring_fwd_kernel")
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": (traffic[0] if traffic else None),
@@ -335,7 +356,7 @@ def run_ours(args):
                             "frac": (alg_fwd + alg_bwd) / (fwd_ms + bwd_ms) / 1e6 / peak_gbs}}
 
     # ---------------- e2e: host buffers through the public API, copies inside the timed region ----
-    e_steps = max(1, min(K, args.e2e_steps))
+    e_steps = K if args.e2e_steps <= 0 else max(1, args.e2e_steps)
     feats_h = [torch.empty(s, pin_memory=True).normal_() for s in shapes]
     gout_h = torch.empty(tuple(grad_out.shape), pin_memory=True).normal_()
     rois_h = torch.from_numpy(d["rois"]).pin_memory()
@@ -394,9 +415,10 @@ def run_ours(args):
             roi_align_forward(maps1[i], rois1, (7, 7), 0.25, 2, out=o1[i])
             roi_align_backward(go1[i], rois1, (1, 256, 200, 272), (7, 7), 0.25, 2, grad_data=g1[i])
         ms = timed(cfg1_step, 4 * max(it // 4, 2))
-        b1 = 2 * (55705600 + 25690112)
+        tb1 = touched_bytes(c1["rois"], np.zeros(512, np.int64), [(200, 272)], [0.25], 1, 256, (7, 7), 2)
+        b1 = (min(55705600, tb1) + 25690112) + (25690112 + 55705600)    # fwd: touched pixels (or the map) + out; bwd: grad_out + every map byte
         secondary["cfg1_roialign_fwd_bwd"] = {"rois_per_s": world * 512 / (ms * 1e-3), "ms": ms,
-                                              "hbm_frac": b1 / ms / 1e6 / peak_gbs, "algorithmic_bytes": b1,
+                                              "hbm_frac": b1 / ms / 1e6 / peak_gbs, "algorithmic_bytes": b1, "touched_bytes": tb1,
                                               "l2_policy": "4 rotating buffer sets (445 MB) > L2"}
         del maps1, g1, go1, o1
         # (b) config 2: RPN proposals, 800x1088, 217 413 anchors/img, batch 2 - and the 8-image shard
@@ -432,9 +454,10 @@ def run_ours(args):
         pairs = IMGS_PER_GPU * anchors.shape[0] * 100
         secondary["cfg4b_max_iou_assigner_b8"] = {"anchors_per_s": world * IMGS_PER_GPU * anchors.shape[0] / (ms * 1e-3), "ms": ms,
                                                    "gt_anchor_pairs_per_s": world * pairs / (ms * 1e-3),
-                                                   "fp32_alu_frac_est": 2 * 20.0 * pairs / (ms * 1e-3) / 74.4e12,
+                                                   "executed_fma_pipe_note": "ncu counts of the two kernels: profiles/README.md (the kernel skips most pairs; "
+                                                                             "no flop-per-pair estimate is reported)",
                                                    "hbm_frac": IMGS_PER_GPU * anchors.shape[0] * 28 / ms / 1e6 / peak_gbs,
-                                                   "bound": "fp32 ALU (two passes x ~20 flop/pair), not HBM"}
+                                                   "bound": "latency / issue (bbox-pruned pair tests), not HBM"}
         # (d) config 4a: mask branch, 14x14 on 128 RoIs/img x 8 imgs (same maps)
         dm = syn.cfg4_mask(batch=IMGS_PER_GPU, first_image=first_image, with_features=False)
         rois_m = torch.from_numpy(dm["rois"]).to(dev)
@@ -444,9 +467,12 @@ def run_ours(args):
             roi_align_fpn_forward(feats, rois_m, (14, 14), scales, 2, out=o_m)
             roi_align_fpn_backward(go_m, rois_m, shapes, (14, 14), scales, 2, grad_feats=grads)
         ms = timed(mask_step, max(it // 2, 3))
-        bm = 2 * (map_bytes + o_m.numel() * 4)
+        lv_m = map_roi_levels(rois_m, 4).cpu().numpy()
+        tbm = touched_bytes(dm["rois"], lv_m, d["feat_shapes"], scales, IMGS_PER_GPU, 256, (14, 14), 2)
+        bm = (min(map_bytes, tbm) + o_m.numel() * 4) + (o_m.numel() * 4 + map_bytes)   # same rule as the headline
         secondary["cfg4a_mask_roialign_14x14_b8"] = {"rois_per_s": world * rois_m.shape[0] / (ms * 1e-3), "ms": ms,
-                                                      "hbm_frac": bm / ms / 1e6 / peak_gbs, "algorithmic_bytes": bm}
+                                                      "hbm_frac": bm / ms / 1e6 / peak_gbs, "algorithmic_bytes": bm,
+                                                      "touched_bytes": tbm}
         # (f) SURVEY 8(f) "next" rows at reference sizes: N1 sampling + target packing of one image's anchors, N2 detection
         # post-processing of 1000 proposals x 81 classes
         from mxdetection_b200.core.bbox import MaxIoUAssigner, RandomSampler, pack_targets
@@ -489,19 +515,50 @@ def run_ours(args):
                                             "stages": "assigner (side stream) || rpn proposals + fpn roialign fwd/bwd, then detection all-gather"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (N(0,1) features / grads, COCO-shaped RoIs, seeded per image)",
             "config": config_dict(world), "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
             "launches_per_step": launches / K, "clocks": clocks, "secondary": secondary}
 
     # ---------------- CPU baseline (rank 0, N=1 only): bounded sample of the same workload --------
     if world == 1 and not args.no_cpu_baseline:
-        n_rois, times, threads = cpu_reference_fpn(2, 3, first_image)
+        n_rois, times, threads, (dd, ref_out, ref_grads) = cpu_reference_fpn(2, 3, first_image, keep=True)
         t = sum(times[1:]) / len(times[1:])
         line["cpu_baseline"] = {"value": n_rois / t, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "2 of the 8 images (1024 RoIs) of the same workload, best-effort 2 timed passes after 1 warm-up: "
                                           "oracle/cpu_ref.c, forward OpenMP over RoIs, backward serial (mxnet 1.3 roi_align.cc structure)",
                                 "seconds_per_pass": t, "host_cpus": os.cpu_count()}
+        # the oracle as CHECKER: the GPU path on the very inputs the CPU port just processed (1e-5 / 1e-4 bars of north_star)
+        f2 = [torch.from_numpy(f).to(dev) for f in dd["feats"]]
+        r2 = torch.from_numpy(dd["rois"]).to(dev)
+        o2 = roi_align_fpn_forward(f2, r2, POOLED, scales, 2)
+        g2 = roi_align_fpn_backward(torch.from_numpy(dd["grad_out"]).to(dev), r2, [tuple(f.shape) for f in dd["feats"]], POOLED, scales, 2)
+        o2 = o2.cpu().numpy()
+        ok_f = bool(np.all(np.abs(o2 - ref_out) <= 1e-5 * np.maximum(1, np.abs(ref_out))))
+        ok_b = all(bool(np.all(np.abs(a.cpu().numpy() - b) <= 1e-4 * np.maximum(1, np.abs(b)))) for a, b in zip(g2, ref_grads))
+        line["verified"] = {"forward_1e-5": ok_f, "backward_1e-4": ok_b, "checksum_out": float(np.float64(o2).sum()),
+                            "checksum_ref": float(np.float64(ref_out).sum()),
+                            "what": "GPU forward + backward of the 2-image sample against the C port's outputs of the cpu_baseline leg"}
+        assert ok_f and ok_b, "bench: GPU output does not match the CPU port"
+        del f2, g2
+        # second, independently compiled CPU baseline: torchvision CPU kernels on BASELINE config 1 and NMS n=2000
+        try:
+            import torchvision
+            c1 = syn.cfg1()
+            x = torch.randn(1, 256, 200, 272, requires_grad=True)
+            rr = torch.from_numpy(c1["rois"])
+            t0 = time.perf_counter(); y = torchvision.ops.roi_align(x, rr, (7, 7), 0.25, 2, aligned=False); t1 = time.perf_counter()
+            y.backward(torch.ones_like(y)); t2 = time.perf_counter()
+            nb = 2000
+            rng_t = np.random.default_rng(7)
+            xy = rng_t.uniform(0, 1200, (nb, 2)); wh = rng_t.uniform(8, 200, (nb, 2))
+            bx = torch.from_numpy(np.concatenate([xy, xy + wh], 1).astype(np.float32)); scs = torch.from_numpy(rng_t.uniform(0, 1, nb).astype(np.float32))
+            t3 = time.perf_counter(); kept = torchvision.ops.nms(bx, scs, 0.7); t4 = time.perf_counter()
+            line["cpu_baseline"]["torchvision_cpu"] = {"cfg1_roi_align_fwd_ms": 1e3 * (t1 - t0), "cfg1_roi_align_bwd_ms": 1e3 * (t2 - t1),
+                                                       "cfg1_rois_per_s": 512 / (t2 - t0), "nms_2000_ms": 1e3 * (t4 - t3), "nms_kept": int(kept.numel()),
+                                                       "threads": torch.get_num_threads(), "version": torchvision.__version__}
+        except Exception as e:      # the second baseline is optional
+            line["cpu_baseline"]["torchvision_cpu"] = {"unavailable": repr(e)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -515,8 +572,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed steps of the host-buffer leg (0 = --steps)")
     ap.add_argument("--secondary-iters", type=int, default=20)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 8 images per GPU (default); strong: 64 images in total (BASELINE config 5), 64/N per GPU")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

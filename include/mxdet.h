@@ -17,8 +17,10 @@
  *  - Outputs of data-dependent length have fixed capacity plus a device
  *    int32 count.
  *  - Return value 0 (MXD_OK) or a negative MXD_E* code; the message is in
- *    the thread-local mxd_last_error().  Re-entrant; no global mutable state
- *    other than the error string and the launch counter.
+ *    the thread-local mxd_last_error().  Re-entrant and callable from several
+ *    host threads: the only global state is the thread-local error string, an
+ *    atomic launch counter and the once-per-device kernel attribute flags
+ *    (dynamic shared-memory opt-in), which are set under a mutex on first use.
  *  - delta ("legacy +1"): 1.0 for the py-faster-rcnn / mmdet-0.5 lineage
  *    (widths x2-x1+1), 0.0 for mx.nd.contrib.box_nms / box_iou.
  *  - All IoU / threshold / label arithmetic is fp32 round-to-nearest without
@@ -181,11 +183,12 @@ int mxd_det_bboxes(const DLTensor* boxes, const DLTensor* deltas, const DLTensor
 /* ---- N1  random sampling + target packing  (SURVEY.md 8(f) "next" row N1: mxdetection/core/anchor + core/bbox,
  *      /root/reference/README.md:16-17; RandomSampler / anchor_target_single / bbox_target_single of mmdet 0.5).
  *      RNG contract: keys (N) f32 in [0,1) are supplied by the caller; the sample is the positives (assigned > 0) /
- *      negatives (assigned == 0) with the LARGEST keys, ties to the lower index.  kp = min(int(num*pos_fraction), N)
+ *      negatives (assigned == 0) with the LARGEST keys, ties to the lower index.  kp = min(int(num*pos_fraction), N), the product taken in double
+ *      (pos_fraction is a double so that the host side's int(num * fraction) and the library agree for 0.7, 0.9, ...)
  *      positives at most, negatives fill up to num (at most neg_pos_ub * max(1, num_pos) when neg_pos_ub >= 0).
  *      pos_inds (kp) / neg_inds (min(num, N)) i32, -1 padded; counts (2) i32 = {num_pos, num_neg}.            */
 size_t mxd_random_sample_workspace_bytes(long long n, int num);
-int mxd_random_sample(const DLTensor* assigned, const DLTensor* keys, int num, float pos_fraction, int neg_pos_ub,
+int mxd_random_sample(const DLTensor* assigned, const DLTensor* keys, int num, double pos_fraction, int neg_pos_ub,
                       DLTensor* pos_inds, DLTensor* neg_inds, DLTensor* counts, void* workspace,
                       size_t workspace_bytes, void* stream);
 /* labels (N) i32, label_weights (N) f32, bbox_targets (N,4), bbox_weights (N,4): zero everywhere except the sampled
@@ -248,6 +251,13 @@ int mxd_rpn_proposals(const DLTensor* const* scores, const DLTensor* const* delt
 int mxd_rpn_proposals_stages(const mxd_rpn_config* cfg, int batch, const void* workspace,
                              size_t workspace_bytes, DLTensor* idx, DLTensor* boxes,
                              DLTensor* keep, DLTensor* counts, void* stream);
+
+/* Tail of the data-parallel path (the detections every GPU hands to the final gather): packs
+ * proposals (B,M,5) [x1,y1,x2,y2,score] + num_valid (B) into ONE buffer packed (B,M+1,6) f32 that a single
+ * all-gather moves - row 0 of image b = {count, image id, 0,0,0,0}, rows 1..M = {image id (-1: padding row),
+ * x1,y1,x2,y2,score}; image id = first_image_id + b.                                                       */
+int mxd_pack_detections(const DLTensor* proposals, const DLTensor* num_valid, int first_image_id,
+                        DLTensor* packed, void* stream);
 
 /* mx.nd.contrib.MultiProposal / Proposal of mxnet 1.3.0 (multi_proposal.cc/.cu; SURVEY.md 8(a) Spec H
  * alt-mode; the call site would be mxdetection/models/rpn_heads, /root/reference/README.md:28).

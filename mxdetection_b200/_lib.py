@@ -179,13 +179,14 @@ _SIG = {
     "mxd_det_bboxes": [_P, _P, _P, POINTER(c_float), POINTER(c_float), c_int, c_int, c_double, c_float, c_float, c_float, c_float,
                        c_int, _P, _P, _P, _P, c_size_t, _P],
     "mxd_random_sample_workspace_bytes": [ctypes.c_longlong, c_int],
-    "mxd_random_sample": [_P, _P, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P],
+    "mxd_random_sample": [_P, _P, c_int, c_double, c_int, _P, _P, _P, _P, c_size_t, _P],
     "mxd_pack_targets": [_P, _P, _P, _P, _P, _P, POINTER(c_float), POINTER(c_float), c_float, _P, _P, _P, _P, _P],
     "mxd_delta2bbox": [_P, _P, _P, POINTER(c_float), POINTER(c_float), c_int, c_int, c_double, _P],
     "mxd_rpn_proposals_workspace_bytes": [POINTER(RpnConfig), c_int],
     "mxd_rpn_proposals_dims": [POINTER(RpnConfig), POINTER(c_int), POINTER(c_int)],
     "mxd_rpn_proposals": [_P, _P, _P, POINTER(RpnConfig), _P, _P, _P, c_size_t, _P],
     "mxd_rpn_proposals_stages": [POINTER(RpnConfig), c_int, _P, c_size_t, _P, _P, _P, _P, _P],
+    "mxd_pack_detections": [_P, _P, c_int, _P, _P],
     "mxd_copy2d_async": [_P, c_size_t, _P, c_size_t, c_size_t, c_size_t, c_int, _P],
     "mxd_multi_proposal_workspace_bytes": [c_int, c_int, c_int, c_int, c_int, c_int],
     "mxd_multi_proposal": [_P, _P, _P, _P, _P, POINTER(c_float), c_int, c_float, c_int, c_int, c_float, c_float, _P,

@@ -15,6 +15,11 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+std::mutex& device_once_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 int check_tensor(const DLTensor* t, const char* name, DT dt, int ndim_lo, int ndim_hi, int* dev) {

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <math.h>
+#include <mutex>
 #include "../../include/mxdet.h"
 
 namespace mxd {
@@ -79,16 +80,35 @@ inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Opt-in dynamic shared memory is a per-DEVICE function attribute: call sites set it once per device
-// (`static unsigned long long seen = 0; if (first_use_on_device(&seen)) cudaFuncSetAttribute(...)`).
-inline bool first_use_on_device(unsigned long long* seen) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const unsigned long long bit = 1ull << (dev & 63);
-  if (*seen & bit) return false;
-  *seen |= bit;
-  return true;
-}
+// Opt-in dynamic shared memory is a per-DEVICE function attribute: call sites set it once per device,
+//   static unsigned long long seen = 0;
+//   DeviceOnce once(&seen); if (once.first()) MXD_CUDA_OK(cudaFuncSetAttribute(...));
+// The guard serialises first use: a second host thread arriving meanwhile waits until the attribute is set (it
+// would otherwise launch with the default limit and fail), later calls take one atomic load.
+std::mutex& device_once_mutex();
+struct DeviceOnce {
+  unsigned long long* seen;
+  unsigned long long bit;
+  bool mine;
+  explicit DeviceOnce(unsigned long long* s) : seen(s), bit(0), mine(false) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bit = 1ull << (dev & 63);
+    if (__atomic_load_n(seen, __ATOMIC_ACQUIRE) & bit) return;
+    device_once_mutex().lock();
+    if (__atomic_load_n(seen, __ATOMIC_RELAXED) & bit) { device_once_mutex().unlock(); return; }
+    mine = true;
+  }
+  DeviceOnce(const DeviceOnce&) = delete;
+  DeviceOnce& operator=(const DeviceOnce&) = delete;
+  bool first() const { return mine; }
+  ~DeviceOnce() {
+    if (mine) {
+      __atomic_fetch_or(seen, bit, __ATOMIC_RELEASE);
+      device_once_mutex().unlock();
+    }
+  }
+};
 
 // ---- device helpers -------------------------------------------------------------
 // float -> uint32 whose unsigned order equals the float order (-0 == +0).

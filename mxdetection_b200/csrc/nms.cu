@@ -356,7 +356,8 @@ int launch_nms_sorted(const NmsSortedArgs& a, cudaStream_t st) {
     MXD_POST_LAUNCH("nms_mask");
   }
   static unsigned long long seen = 0;
-  if (first_use_on_device(&seen)) {
+  DeviceOnce once_seen(&seen);
+  if (once_seen.first()) {
     MXD_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResolveSmemMax));
     MXD_CUDA_OK(cudaFuncSetAttribute(nms_resolve_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResolveSmemMax));
   }
@@ -491,8 +492,9 @@ __global__ void det_candidates_kernel(const float* __restrict__ boxes, int box_c
   if (deltas) {
     const float* dp = deltas + (size_t)i * delta_cols + (delta_cols == 4 ? 0 : 4 * c);
     b = decode_box(b, make_float4(dp[0], dp[1], dp[2], dp[3]), means.v, stds.v, max_ratio, hmax, wmax, clip != 0);
-    if (scale != 1.0f) b = make_float4(__fdiv_rn(b.x, scale), __fdiv_rn(b.y, scale), __fdiv_rn(b.z, scale), __fdiv_rn(b.w, scale));
   }
+  // BBoxHead.get_det_bboxes rescales in both branches (decoded or rois-only boxes)
+  if (scale != 1.0f) b = make_float4(__fdiv_rn(b.x, scale), __fdiv_rn(b.y, scale), __fdiv_rn(b.z, scale), __fdiv_rn(b.w, scale));
   ob[m] = b;
   os[m] = score[(size_t)i * C + c];
   oid[m] = c - 1;

@@ -96,6 +96,25 @@ __global__ void __launch_bounds__(kCollectThreads, 1) rpn_collect_kernel(Collect
   if (tid == 0 && part == 0) a.num_valid[b] = nout;
 }
 
+// Tail of the data-parallel path: per-image proposals -> ONE fixed-capacity buffer that a single
+// all-gather moves: row 0 of image b = {count, image id, 0, 0, 0, 0}, rows 1..max_num = {image id | -1 for padding,
+// x1, y1, x2, y2, score}.
+__global__ void pack_detections_kernel(const float* __restrict__ props, const int* __restrict__ num_valid, int B, int M,
+                                       int first_image_id, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * (M + 1)) return;
+  const int b = i / (M + 1), r = i - b * (M + 1);
+  const int nv = num_valid[b];
+  float* o = out + (size_t)i * 6;
+  if (r == 0) {
+    o[0] = (float)nv; o[1] = (float)(first_image_id + b); o[2] = o[3] = o[4] = o[5] = 0.0f;
+    return;
+  }
+  const float* p = props + ((size_t)b * M + (r - 1)) * 5;
+  o[0] = (r - 1 < nv) ? (float)(first_image_id + b) : -1.0f;
+  o[1] = p[0]; o[2] = p[1]; o[3] = p[2]; o[4] = p[3]; o[5] = p[4];
+}
+
 struct RpnWs {
   int* idx; float* vals; float4* boxes; uint8_t* valid; int* cnt; u64* mask; int* keep; int* keep_cnt;
   void* sortws; size_t sort_bytes;      // chunk-sort scratch when nms_pre exceeds MXD_SORT_CAP
@@ -236,11 +255,31 @@ int mxd_rpn_proposals(const DLTensor* const* scores, const DLTensor* const* delt
   c.out = dptr<float>(proposals); c.num_valid = dptr<int>(num_valid);
   const int smem = std::max(L * ks, 1) * (int)sizeof(float);
   static unsigned long long seen = 0;
-  if (first_use_on_device(&seen))
+  DeviceOnce once_seen(&seen);
+  if (once_seen.first())
     MXD_CUDA_OK(cudaFuncSetAttribute(rpn_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kCollectCap * (int)sizeof(float)));
   rpn_collect_kernel<<<dim3(B, 4), kCollectThreads, smem, st>>>(c);
   MXD_POST_LAUNCH("rpn_collect");
+  return MXD_OK;
+}
+
+int mxd_pack_detections(const DLTensor* proposals, const DLTensor* num_valid, int first_image_id, DLTensor* packed,
+                        void* stream) {
+  int dev = -1, rc;
+  if ((rc = check_tensor(proposals, "proposals", F32, 3, 3, &dev))) return rc;
+  if ((rc = check_tensor(num_valid, "num_valid", I32, 1, 1, &dev))) return rc;
+  if ((rc = check_tensor(packed, "packed", F32, 3, 3, &dev))) return rc;
+  const int B = (int)proposals->shape[0], M = (int)proposals->shape[1];
+  MXD_REQUIRE(proposals->shape[2] == 5 && num_valid->shape[0] == B, MXD_EINVAL, "proposals (B,M,5) / num_valid (B)");
+  MXD_REQUIRE(packed->shape[0] == B && packed->shape[1] == M + 1 && packed->shape[2] == 6, MXD_EINVAL,
+              "packed must be (B=%d, M+1=%d, 6)", B, M + 1);
+  if (B == 0) return MXD_OK;
+  const long long total = (long long)B * (M + 1);
+  MXD_REQUIRE(total < (1ll << 31), MXD_ENOTSUP, "too many rows");
+  pack_detections_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+      dptr<float>(proposals), dptr<int>(num_valid), B, M, first_image_id, dptr<float>(packed));
+  MXD_POST_LAUNCH("pack_detections");
   return MXD_OK;
 }
 

@@ -1115,15 +1115,11 @@ size_t plane_workspace_bytes(int R, int N, int L, const int* Hs, const int* Ws, 
   return need;
 }
 
-static int num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
+static int num_sms() {      // per call: the current device may differ between calls
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms > 0 ? sms : 148;
 }
 
 static int run_planner(const FpnDesc& d, const PlanCfg& c, const PlanWs& w, const float* rois, const int* levels,
@@ -1157,7 +1153,8 @@ int plane_forward(const FpnDesc& d, const float* rois, const int* levels, float*
     plan_pack_kernel<<<(R * c.s4_ent + 255) / 256, 256, 0, st>>>(c, w, R);
     MXD_POST_LAUNCH("roi_align_plan_pack");
     static unsigned long long seen4 = 0;
-    if (first_use_on_device(&seen4)) {
+    DeviceOnce once_seen4(&seen4);
+  if (once_seen4.first()) {
       MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_stream_fwd_kernel<7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemLimit));
       MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_stream_fwd_kernel<14, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1176,7 +1173,8 @@ int plane_forward(const FpnDesc& d, const float* rois, const int* levels, float*
                   : (sr == 2) ? roi_align_plane_fwd_kernel<2> : roi_align_plane_fwd_kernel<0>;
   static unsigned long long seen[3] = {0, 0, 0};
   const int ki = tap ? 2 : sr == 2 ? 0 : 1;
-  if (first_use_on_device(&seen[ki]))
+  DeviceOnce once_k(&seen[ki]);
+  if (once_k.first())
     MXD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   kern<<<num_sms() * c.ctas_per_sm, c.threads, c.smem_bytes, st>>>(d, c, w, rois, levels, out);
   MXD_POST_LAUNCH("roi_align_plane_fwd");

@@ -730,7 +730,8 @@ int ring_forward(const FpnDesc& d, const float* rois, const int* levels, float* 
   rg_plan_pack_kernel<<<(R + 7) / 8, 256, 0, st>>>(c, w, R);
   MXD_POST_LAUNCH("roi_align_rg_plan_pack");
   static unsigned long long seen = 0;
-  if (first_use_on_device(&seen))
+  DeviceOnce once_seen(&seen);
+  if (once_seen.first())
     MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_ring_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRgSmem));
   roi_align_ring_fwd_kernel<<<sms, kRgThreads, kRgSmem, st>>>(d, c, maps, w, rois, levels, out);
   MXD_POST_LAUNCH("roi_align_ring_fwd");

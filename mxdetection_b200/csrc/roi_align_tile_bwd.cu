@@ -668,7 +668,8 @@ int tile_backward(const FpnDesc& d, const float* rois, const int* levels, const 
   tplan_group_kernel<<<1, 1024, 0, st>>>(c, w, R);
   MXD_POST_LAUNCH("roi_align_tplan_group");
   static unsigned long long seen = 0;
-  if (first_use_on_device(&seen)) {
+  DeviceOnce once_seen(&seen);
+  if (once_seen.first()) {
     MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_tile_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem));
     MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_tile_bwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem));
   }

@@ -74,7 +74,7 @@ size_t mxd_random_sample_workspace_bytes(long long n, int num) {
   return sample_ws_layout(n, num > 0 ? num : 1, &a, &b);
 }
 
-int mxd_random_sample(const DLTensor* assigned, const DLTensor* keys, int num, float pos_fraction, int neg_pos_ub,
+int mxd_random_sample(const DLTensor* assigned, const DLTensor* keys, int num, double pos_fraction, int neg_pos_ub,
                       DLTensor* pos_inds, DLTensor* neg_inds, DLTensor* counts, void* workspace,
                       size_t workspace_bytes, void* stream) {
   int dev = -1, rc;
@@ -86,7 +86,7 @@ int mxd_random_sample(const DLTensor* assigned, const DLTensor* keys, int num, f
   const long long n = assigned->shape[0];
   MXD_REQUIRE(keys->shape[0] == n && n < (1ll << 31), MXD_EINVAL, "keys must be (N)");
   MXD_REQUIRE(num >= 0 && num <= MXD_SORT_CAP, MXD_ENOTSUP, "sample size %d exceeds the sort capacity %d", num, MXD_SORT_CAP);
-  const int kp = (int)std::min<long long>((long long)((double)num * (double)pos_fraction), n);
+  const int kp = (int)std::min<long long>((long long)((double)num * pos_fraction), n);
   const int kn = (int)std::min<long long>(num, n);
   MXD_REQUIRE(pos_inds->shape[0] == kp && neg_inds->shape[0] == kn && counts->shape[0] == 2, MXD_EINVAL,
               "pos_inds / neg_inds / counts must be (%d) / (%d) / (2)", kp, kn);

@@ -570,7 +570,8 @@ int launch_topk(const TopkParams& p, cudaStream_t st, void* long_ws, size_t long
                 "top-k of %d rows needs a %zu-byte sort workspace (got %zu)", kbig_all, need, long_ws_bytes);
     MXD_REQUIRE(S <= 65535 && nchunks >= 1, MXD_ENOTSUP, "too many top-k segments");
     const int smem = kCap * (int)sizeof(u64);
-    if (first_use_on_device(&seen_long))
+    DeviceOnce once_seen_long(&seen_long);
+  if (once_seen_long.first())
       MXD_CUDA_OK(cudaFuncSetAttribute(topk_chunk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     topk_chunk_sort_kernel<<<dim3(nchunks, S), kTopkThreads, smem, st>>>(p, static_cast<u64*>(long_ws), nchunks);
     MXD_POST_LAUNCH("topk_chunk_sort");
@@ -582,7 +583,8 @@ int launch_topk(const TopkParams& p, cudaStream_t st, void* long_ws, size_t long
   for (int l = 0; l < p.num_levels; ++l) big = big || p.n[l] > kCap;
   static unsigned long long seen = 0;
   const int smem = kCap * (int)sizeof(u64);
-  if (first_use_on_device(&seen)) {
+  DeviceOnce once_seen(&seen);
+  if (once_seen.first()) {
     MXD_CUDA_OK(cudaFuncSetAttribute(topk_segment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     MXD_CUDA_OK(cudaFuncSetAttribute(topk_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * smem));
   }

@@ -15,11 +15,12 @@ def _det_call(boxes, deltas, scores, means, stds, img_shape, scale_factor, score
     m = n * (C - 1)
     k = min(m, L.MXD_SORT_CAP)
     cap = min(k, max_num) if max_num > 0 else k
-    dets = torch.zeros((cap, 5), dtype=torch.float32, device=dev)
-    labels = torch.full((cap,), -1, dtype=torch.int32, device=dev)
-    num = torch.zeros(1, dtype=torch.int32, device=dev)
     if m == 0 or cap == 0:
-        return dets, labels, num
+        return (torch.zeros((cap, 5), dtype=torch.float32, device=dev), torch.full((cap,), -1, dtype=torch.int32, device=dev),
+                torch.zeros(1, dtype=torch.int32, device=dev))
+    dets = torch.empty((cap, 5), dtype=torch.float32, device=dev)       # the library writes every row (zeros / -1 past num)
+    labels = torch.empty((cap,), dtype=torch.int32, device=dev)
+    num = torch.empty(1, dtype=torch.int32, device=dev)
     ws = L.workspace(L.lib.mxd_det_bboxes_workspace_bytes(n, C, int(max_num)), dev, "det")
     ih, iw = (int(img_shape[0]), int(img_shape[1])) if img_shape is not None else (0, 0)
     L.call("mxd_det_bboxes", L.dl(boxes.float().contiguous()), L.dl(None if deltas is None else deltas.float().contiguous()),
@@ -41,7 +42,8 @@ def get_det_bboxes(rois, cls_score, bbox_pred, img_shape, scale_factor=1.0, scor
                    target_means=(0, 0, 0, 0), target_stds=(0.1, 0.1, 0.2, 0.2), reg_class_agnostic=False):
     """BBoxHead.get_det_bboxes: rois (n,5), cls_score (n,C) ALREADY softmaxed, bbox_pred (n,4) or (n,4*C) or None."""
     boxes = rois[:, 1:]
-    if bbox_pred is None:
-        return _det_call(boxes, None, cls_score, target_means, target_stds, None, 1.0, score_thr, iou_thr, 1.0, max_per_img)
+    if bbox_pred is None:      # rois are the final boxes: no clip, but still rescaled to the original image frame
+        return _det_call(boxes, None, cls_score, target_means, target_stds, None, scale_factor, score_thr, iou_thr, 1.0,
+                         max_per_img)
     return _det_call(boxes, bbox_pred, cls_score, target_means, target_stds, img_shape, scale_factor, score_thr, iou_thr, 1.0,
                      max_per_img)

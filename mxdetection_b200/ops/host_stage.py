@@ -62,6 +62,8 @@ class HostRoIStage:
         if b.size and np.any(np.diff(b) < 0):
             raise ValueError("HostRoIStage: RoIs must be grouped by image (non-decreasing batch index)")
         N = self.shapes[0][0]
+        if b.size and (b.min() < 0 or b.max() >= N):
+            raise ValueError("HostRoIStage: batch indices must lie in [0, %d) (got %d .. %d)" % (N, b.min(), b.max()))
         counts = np.bincount(b, minlength=N)[:N] if b.size else np.zeros(N, np.int64)
         if counts.max(initial=0) > self.max_rois:
             raise ValueError("HostRoIStage: %d RoIs on one image, capacity %d" % (counts.max(), self.max_rois))

@@ -52,7 +52,9 @@ def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_thr, max_num=-1, d
 def get_det_bboxes(rois, cls_score, bbox_pred, img_shape, scale_factor=1.0, score_thr=0.05, iou_thr=0.5, max_per_img=100,
                    target_means=(0, 0, 0, 0), target_stds=(0.1, 0.1, 0.2, 0.2)):
     n, C = cls_score.shape
-    if bbox_pred.shape[1] == 4:
+    if bbox_pred is None:          # rois are final (mmdet 0.5: `bboxes = rois[:, 1:]`), still divided by scale_factor
+        b = np.asarray(rois, F)[:, 1:].copy()
+    elif bbox_pred.shape[1] == 4:
         b = delta2bbox(rois[:, 1:], bbox_pred, target_means, target_stds, img_shape)
     else:
         r = np.repeat(rois[:, None, 1:], C, 1).reshape(-1, 4)

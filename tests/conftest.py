@@ -8,7 +8,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+LIB_ERROR = None      # why libmxdet_sm100.so could not be built (no nvcc on a CPU-only checkout), else None
+
+
 def pytest_configure(config):
+    global LIB_ERROR
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with `-m gpu` through gpurun")
     # the product library and the C oracle are build artefacts; make sure they exist before collection
     # build.py is loaded by path: importing the package itself needs the built library (no CPU fallback)
@@ -16,13 +20,27 @@ def pytest_configure(config):
     spec = importlib.util.spec_from_file_location("_mxd_build", os.path.join(ROOT, "mxdetection_b200", "build.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    mod.build_library()
+    try:
+        mod.build_library()
+    except (OSError, RuntimeError) as e:      # nvcc missing / failing: the pure-oracle tests still run
+        LIB_ERROR = "libmxdet_sm100.so not built: %s" % str(e).splitlines()[0]
     from oracle import cref
     cref.build()
 
 
 def pytest_collection_modifyitems(config, items):
     import torch
+    if LIB_ERROR is not None:       # everything that imports the package needs the library; say so instead of erroring
+        needs = pytest.mark.skip(reason=LIB_ERROR)
+        for it in items:
+            src = ""
+            try:
+                import inspect
+                src = inspect.getsource(it.function)
+            except Exception:
+                pass
+            if "gpu" in it.keywords or "mxdetection_b200" in src or it.fspath.basename in ("test_abi.py", "test_parallel_gloo.py"):
+                it.add_marker(needs)
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")

@@ -30,6 +30,19 @@ def test_library_exports_every_declared_symbol():
     assert cref.lib().ora_sizeof_rpn_config() == ctypes.sizeof(cref.RpnConfig)
 
 
+def test_header_is_c99_and_the_abi_works_without_python(tmp_path):
+    """include/mxdet.h compiled as C99 (-Wall -Wextra -pedantic -Werror) into a program that dlopen()s the library and
+    calls the host-only entry points: version, struct size, workspace queries, and the loud refusal of a CPU tensor."""
+    from mxdetection_b200 import _lib as L
+    import subprocess
+    exe = str(tmp_path / "abi_smoke")
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                         os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-ldl", "-o", exe], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([exe, L.LIB_PATH], capture_output=True, text=True)
+    assert run.returncode == 0 and "abi ok" in run.stdout, run.stdout + run.stderr
+
+
 def test_built_for_sm100a_only():
     from mxdetection_b200 import _lib as L
     import subprocess

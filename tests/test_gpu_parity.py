@@ -805,7 +805,7 @@ def test_random_sampler_and_target_packing_n1():
     ra, _, _ = oracle.max_iou_assign(anchors, gts, None, 0.7, 0.3, 0.3)
     keys = rng.random(anchors.shape[0]).astype(F)
     keys[::7] = keys[3]                                            # ties
-    for num, frac, ub in ((256, 0.5, -1), (64, 0.25, 3), (8, 0.5, 0)):
+    for num, frac, ub in ((256, 0.5, -1), (64, 0.25, 3), (8, 0.5, 0), (100, 0.7, -1), (200, 0.35, -1), (10, 0.9, 2)):   # 0.7 / 0.35 / 0.9 round down as fp32
         s = RandomSampler(num, frac, ub).sample(a.gt_inds, T(keys))
         pos, neg = oracle.targets.random_sample(ra, keys, num, frac, ub)
         gp = N(s.pos_inds); gn = N(s.neg_inds)
@@ -832,6 +832,12 @@ def test_multiclass_nms_and_det_bboxes_n2():
         k = int(num.item())
         assert k == len(rl) and np.array_equal(N(labels)[:k], rl) and np.all(N(labels)[k:] == -1)
         assert np.abs(N(dets)[:k] - rd).max() <= 1e-5 and np.array_equal(N(dets)[:k, 4], rd[:, 4])
+    # rescale (scale_factor != 1) in both branches: decoded boxes and rois-only (bbox_pred None)
+    for pred_ in (pred, None):
+        dets, labels, num = get_det_bboxes(T(rois), T(score), None if pred_ is None else T(pred_), (600, 800), 1.6, 0.05, 0.5, 100)
+        rd, rl = oracle.targets.get_det_bboxes(rois, score, pred_, (600, 800), 1.6, 0.05, 0.5, 100)
+        k = int(num.item())
+        assert k == len(rl) and np.array_equal(N(labels)[:k], rl) and np.abs(N(dets)[:k] - rd).max() <= 1e-5
     d2, l2, n2 = multiclass_nms(T(rois[:, 1:]), T(score), 2.0, 0.5, 10)          # nothing passes the threshold
     assert int(n2.item()) == 0 and np.all(N(l2) == -1)
 
@@ -957,3 +963,70 @@ def test_pipeline_is_cuda_graph_capturable():
         g.replay()
         st.synchronize()
     assert torch.equal(props, eager)
+
+
+# ============================================================ SURVEY 8(e): tail gather ==
+def test_pack_detections_layout():
+    from mxdetection_b200.parallel import pack_detections, unpack_detections
+    from test_parallel_gloo import pack_reference
+    rng = np.random.default_rng(3)
+    props = rng.standard_normal((5, 7, 5)).astype(F)
+    nv = np.array([7, 0, 3, 1, 6], np.int32)
+    packed = pack_detections(T(props), T(nv), 40)
+    assert np.array_equal(N(packed), pack_reference(torch.from_numpy(props), torch.from_numpy(nv), 40).numpy())
+    dets, counts, ids = unpack_detections(packed)
+    assert N(counts).tolist() == nv.tolist() and N(ids).tolist() == [40, 41, 42, 43, 44]
+
+
+def _nccl_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    try:
+        import torch.distributed as dist
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        from mxdetection_b200.models.rpn_heads import ProposalConfig, RPNHead
+        from mxdetection_b200.parallel import gather_detections, shard_range
+        n_img = 2 * world
+        d = syn.rpn_inputs(11, n_img, 160, 224)
+        lo, hi = shard_range(n_img, rank, world)
+        dev = "cuda:%d" % rank
+        sc = [torch.from_numpy(s[lo:hi]).to(dev) for s in d["scores"]]
+        dl = [torch.from_numpy(x[lo:hi]).to(dev) for x in d["deltas"]]
+        shp = torch.from_numpy(d["img_shapes"][lo:hi]).to(dev)
+        props, nv = RPNHead().get_proposals(sc, dl, d["feat_shapes"], shp, ProposalConfig(nms_pre=300, nms_post=100, max_num=150, nms_thr=0.7))
+        dets, counts = gather_detections(props, nv, first_image_id=lo)
+        torch.cuda.synchronize()
+        q.put((rank, dets.cpu().numpy(), counts.cpu().numpy()))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:
+        q.put((rank, repr(e), None))
+
+
+def test_nccl_gather_equals_single_gpu_concatenation():
+    """the detections gathered over NCCL from W GPUs (2 images each) equal, bit for bit, the proposals of
+    one GPU run over all 2W images.  Needs >= 2 GPUs (gpurun --gpus N); on a one-GPU box it is skipped."""
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    from mxdetection_b200.models.rpn_heads import ProposalConfig, RPNHead
+    from mxdetection_b200.parallel import pack_detections, unpack_detections
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    n_img = 2 * world
+    d = syn.rpn_inputs(11, n_img, 160, 224)
+    props, nv = RPNHead().get_proposals([T(s) for s in d["scores"]], [T(x) for x in d["deltas"]], d["feat_shapes"], T(d["img_shapes"]),
+                                        ProposalConfig(nms_pre=300, nms_post=100, max_num=150, nms_thr=0.7))
+    ref_d, ref_c, _ = unpack_detections(pack_detections(props, nv, 0))
+    for rank, dets, counts in res:
+        assert counts is not None, dets
+        assert np.array_equal(dets, N(ref_d)) and np.array_equal(counts, N(ref_c)), "rank %d" % rank

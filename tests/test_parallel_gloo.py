@@ -7,17 +7,32 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
+def pack_reference(proposals, num_valid, first_image_id):
+    """Layout of mxd_pack_detections restated on the CPU: (b,m,5) + (b) -> (b,m+1,6)."""
+    b, m, _ = proposals.shape
+    out = torch.zeros((b, m + 1, 6), dtype=torch.float32)
+    for i in range(b):
+        nv = int(num_valid[i])
+        out[i, 0, 0] = nv; out[i, 0, 1] = first_image_id + i
+        out[i, 1:, 1:] = proposals[i]
+        out[i, 1:, 0] = -1.0
+        out[i, 1:1 + nv, 0] = first_image_id + i
+    return out
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     try:
         dist.init_process_group("gloo", rank=rank, world_size=world)
-        from mxdetection_b200.parallel import gather_detections, shard_range
+        from mxdetection_b200.parallel import all_gather_packed, shard_range, unpack_detections
         lo, hi = shard_range(6, rank, world)
         rng = np.random.default_rng(100)
         allp = torch.from_numpy(rng.standard_normal((6, 5, 5)).astype(np.float32))
         alln = torch.tensor([5, 0, 3, 1, 5, 2], dtype=torch.int32)
-        out, cnt = gather_detections(allp[lo:hi], alln[lo:hi], first_image_id=lo)
-        q.put((rank, out.numpy(), cnt.numpy()))
+        # the packing kernel needs a GPU (tests/test_gpu_parity.py checks it against this layout); here the host logic:
+        # shard -> one all-gather of the packed blocks -> views
+        out, cnt, ids = unpack_detections(all_gather_packed(pack_reference(allp[lo:hi], alln[lo:hi], lo)))
+        q.put((rank, out.numpy(), cnt.numpy().astype(np.int32)))
         dist.barrier()
         dist.destroy_process_group()
     except Exception as e:   # surface the failure instead of hanging the parent on q.get
@@ -35,7 +50,6 @@ def test_shard_range_covers_everything():
 
 
 def test_gather_detections_world2_gloo():
-    from mxdetection_b200.parallel import pack_detections
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + os.getpid() % 2000
@@ -49,7 +63,7 @@ def test_gather_detections_world2_gloo():
     rng = np.random.default_rng(100)
     allp = torch.from_numpy(rng.standard_normal((6, 5, 5)).astype(np.float32))
     alln = torch.tensor([5, 0, 3, 1, 5, 2], dtype=torch.int32)
-    expect = pack_detections(allp, alln, 0).numpy()      # == concatenation of the single-process result
+    expect = pack_reference(allp, alln, 0).numpy()[:, 1:]      # == concatenation of the single-process result
     for rank, out, cnt in res:
         assert cnt is not None, out
         assert np.array_equal(out, expect) and cnt.tolist() == alln.tolist()
