@@ -110,6 +110,25 @@ struct DeviceOnce {
   }
 };
 
+// ---- programmatic dependent launch ---------------------------------------------------
+// A kernel launched with launch_pdl may be scheduled while its predecessor in the stream is still running (the launch
+// latency and the kernel's own prologue overlap the predecessor's tail); it must call pdl_wait() before it touches
+// anything the predecessor wrote.  Planner -> persistent-kernel chains use it: 3-4 us per kernel boundary.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // ---- device helpers -------------------------------------------------------------
 // float -> uint32 whose unsigned order equals the float order (-0 == +0).
 __device__ __forceinline__ uint32_t f32_orderable(float x) {

@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(256) rg_plan_rois_kernel(FpnDesc d, RgCfg c, R
                                                             const int* __restrict__ levels, int R) {
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_wait();                       // the workspace memset (and whatever produced rois) is complete
+  pdl_launch_dependents();
   if (n >= R) return;
   const RoiGeom g = roi_geom(d, rois, levels, n, 7, 7, 2, c.finest);
   const RgLevel& v = c.lv[g.ok ? g.lvl : 0];
@@ -223,6 +225,8 @@ __global__ void __launch_bounds__(256) rg_plan_pack_kernel(RgCfg c, RgWs w, int 
   __shared__ int s_start[kRgMaxGroups];
   __shared__ int s_part[256];
   const int tid = threadIdx.x;
+  pdl_wait();                       // the RoI plans are complete
+  pdl_launch_dependents();
   const int per = (c.NB + 255) / 256;
   int sum = 0;
   for (int i = tid * per; i < min(c.NB, (tid + 1) * per); ++i) sum += w.cnt[i];
@@ -537,6 +541,7 @@ roi_align_ring_fwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
   if (tid < 32) ctl->prog[tid] = tid;       // warp w starts with job w
   if (tid < kRgSlotsMax) ctl->thresh[tid] = 0;
   __syncthreads();
+  pdl_wait();                               // the planner's tables and group counts are complete
   const int lane = tid & 31, cw = tid >> 5;
   if (cw == kRgWarps) {
     rg_producer(d, c, maps, w, ctl, arena, lane);
@@ -725,15 +730,16 @@ int ring_forward(const FpnDesc& d, const float* rois, const int* levels, float* 
   MXD_REQUIRE(((uintptr_t)ws & 255) == 0, MXD_EINVAL, "workspace must be 256-byte aligned");
   const size_t zbytes = (size_t)((char*)w.start - (char*)w.hdr);      // hdr, cnt, rmax
   MXD_CUDA_OK(cudaMemsetAsync(w.hdr, 0, zbytes, st));
-  rg_plan_rois_kernel<<<(R * 32 + 255) / 256, 256, 0, st>>>(d, c, w, rois, levels, R);
+  MXD_CUDA_OK(launch_pdl(rg_plan_rois_kernel, dim3((R * 32 + 255) / 256), dim3(256), 0, st, d, c, w, rois, levels, R));
   MXD_POST_LAUNCH("roi_align_rg_plan_rois");
-  rg_plan_pack_kernel<<<(R + 7) / 8, 256, 0, st>>>(c, w, R);
+  MXD_CUDA_OK(launch_pdl(rg_plan_pack_kernel, dim3((R + 7) / 8), dim3(256), 0, st, c, w, R));
   MXD_POST_LAUNCH("roi_align_rg_plan_pack");
   static unsigned long long seen = 0;
   DeviceOnce once_seen(&seen);
   if (once_seen.first())
     MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_ring_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRgSmem));
-  roi_align_ring_fwd_kernel<<<sms, kRgThreads, kRgSmem, st>>>(d, c, maps, w, rois, levels, out);
+  MXD_CUDA_OK(launch_pdl(roi_align_ring_fwd_kernel, dim3(sms), dim3(kRgThreads), (size_t)kRgSmem, st, d, c, maps, w, rois,
+                         levels, out));
   MXD_POST_LAUNCH("roi_align_ring_fwd");
   *handled = 1;
   return MXD_OK;

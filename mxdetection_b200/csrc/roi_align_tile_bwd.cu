@@ -28,7 +28,11 @@
 
 namespace mxd {
 
-constexpr int kTbWarps = 25;                       // consumer warps; warp w owns tile row w (a tile has at most 25 rows)
+#ifndef MXD_TB_R
+#define MXD_TB_R 1
+#endif
+constexpr int kTbR = MXD_TB_R;                     // tile rows per consumer warp (1; 2 measured 5 % slower: fewer, fatter warps)
+constexpr int kTbWarps = (25 + kTbR - 1) / kTbR;   // consumer warps; warp w owns tile rows R*w .. R*w+R-1 (a tile has <= 25 rows)
 constexpr int kTbProducers = 4;                    // producer warps: message m is built by producer m mod 4 (one warp needs
                                                    // ~1500 cycles per message - two bulk copies, a barrier wait, the packed
                                                    // bins - and left the consumers waiting 30 % of the time)
@@ -37,7 +41,7 @@ constexpr int kTbMaxStages = 16;                   // ring depth is per configur
 constexpr int kTbMaxHfCap = 256;                   // rows of the dense per-RoI row table: min(cap, tallest map)
 constexpr int kTbPix = 33;                         // words per tile pixel (32 channels + 1 pad)
 constexpr int kTbMaxTiles = 64;                    // tiles one RoI may intersect
-constexpr int kTbMaxTh = kTbWarps;
+constexpr int kTbMaxTh = kTbR * kTbWarps;
 constexpr int kTbMaxTw = 48;
 constexpr int kTbRowWords = (kTbMaxTw + 1) * kTbPix;   // fixed row pitch: 48 columns + the trash column
 constexpr int kTbTrash = kTbMaxTw * kTbPix * 4;        // byte offset of the trash pixel inside a row
@@ -135,6 +139,8 @@ __global__ void __launch_bounds__(256) tplan_rois_kernel(FpnDesc d, TCfg c, TWs 
                                                           const int* __restrict__ levels, int R) {
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_wait();                       // the workspace memset (and whatever produced rois) is complete
+  pdl_launch_dependents();
   if (n >= R) return;
   const unsigned full = 0xffffffffu;
   const RoiGeom g = roi_geom(d, rois, levels, n, c.PH, c.PW, c.sr, c.finest);
@@ -242,6 +248,8 @@ __global__ void __launch_bounds__(1024) tplan_group_kernel(TCfg c, TWs w, int R)
   __shared__ int s_part[1024];
   __shared__ int s_pos[kTbSmemTiles];      // next free slot of every tile's list
   const int tid = threadIdx.x;
+  pdl_wait();                       // the RoI plans are complete
+  pdl_launch_dependents();
   const bool in_smem = c.NT <= kTbSmemTiles;
   const int per = (c.NT + 1023) / 1024;
   int sum = 0;
@@ -420,17 +428,14 @@ __device__ __forceinline__ void tb_producer(const FpnDesc& d, const TCfg& c, con
 #endif
 }
 
-// One tile row of one RoI for this lane's channel: h[pw] = sum_ph Wy[row][ph] * g[ph][pw], then the
-// (up to) 4 distinct columns of every bin get w_k * h[pw] with plain read-modify-writes - the row
-// belongs to this warp, and distinct columns let the 4 loads issue before the 4 stores.
+// One tile row of one RoI for this lane's channel, part 1: h[pw] = sum_ph Wy[row][ph] * g[ph][pw].  Returns false
+// when no bin feeds the row.
 template <int PW>
-__device__ __forceinline__ void tb_row(const float* __restrict__ gl, const uint2* __restrict__ rt,
-                                       const uint4* __restrict__ xt, char* rowp, float two_ic) {
+__device__ __forceinline__ bool tb_h(const float* __restrict__ gl, const uint2* __restrict__ rt, float (&h)[PW]) {
   const uint2 q0 = rt[0];                    // {first bin | nbins << 8, w0}
   const int nph = (int)((q0.x >> 8) & 0xffu);
-  if (nph == 0) return;
+  if (nph == 0) return false;
   const float* gp = gl + (int)(q0.x & 0xffu) * PW;
-  float h[PW];
   // g[lane * bins + bin]: conflict-free 32-bit loads when bins is odd (7x7); for 14x14 (bins = 196, lane stride
   // = 4 banks) 64-bit loads of bin pairs halve the 4-way conflicts (rows of PW = 14 floats are 8-byte aligned)
   auto grow = [&](int k, float (&gv)[PW]) {
@@ -482,21 +487,38 @@ __device__ __forceinline__ void tb_row(const float* __restrict__ gl, const uint2
       }
     }
   }
+  return true;
+}
+
+// Part 2, for the warp's two rows at once: the (up to) 4 distinct columns of every bin get w_k * h[pw] with plain
+// read-modify-writes - the rows belong to this warp, and distinct columns let the loads issue before the stores.
+// The packed bin {w1, w2, w3, 4 column bytes} is fetched and unpacked once for both rows.  (Skipping the slots that
+// point at the trash column - 19 % of them on the benchmark workload - with warp-uniform branches measured 5 %
+// SLOWER: 0.437 vs 0.414 ms; the straight-line bin body schedules better than it saves.)
+template <int PW, bool A, bool B>
+__device__ __forceinline__ void tb_rmw2(const float (&hA)[PW], const float (&hB)[PW], const uint4* __restrict__ xt,
+                                        char* rowA, float two_ic) {
 #pragma unroll
   for (int pw = 0; pw < PW; ++pw) {
     const uint4 e = xt[pw];
     const float w1 = __uint_as_float(e.x), w2 = __uint_as_float(e.y), w3 = __uint_as_float(e.z);
     const float w0 = two_ic - ((w1 + w2) + w3);
-    float* p0 = reinterpret_cast<float*>(rowp + (e.w & 0xffu) * (kTbPix * 4));
-    float* p1 = reinterpret_cast<float*>(rowp + ((e.w >> 8) & 0xffu) * (kTbPix * 4));
-    float* p2 = reinterpret_cast<float*>(rowp + ((e.w >> 16) & 0xffu) * (kTbPix * 4));
-    float* p3 = reinterpret_cast<float*>(rowp + (e.w >> 24) * (kTbPix * 4));
-    const float v0 = *p0, v1 = *p1, v2 = *p2, v3 = *p3;
-    const float hv = h[pw];
-    *p0 = fmaf(w0, hv, v0);
-    *p1 = fmaf(w1, hv, v1);
-    *p2 = fmaf(w2, hv, v2);
-    *p3 = fmaf(w3, hv, v3);
+    float* p0 = reinterpret_cast<float*>(rowA + (e.w & 0xffu) * (kTbPix * 4));
+    float* p1 = reinterpret_cast<float*>(rowA + ((e.w >> 8) & 0xffu) * (kTbPix * 4));
+    float* p2 = reinterpret_cast<float*>(rowA + ((e.w >> 16) & 0xffu) * (kTbPix * 4));
+    float* p3 = reinterpret_cast<float*>(rowA + (e.w >> 24) * (kTbPix * 4));
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+    if (A) { a0 = *p0; a1 = *p1; a2 = *p2; a3 = *p3; }
+    if (B) { b0 = p0[kTbRowWords]; b1 = p1[kTbRowWords]; b2 = p2[kTbRowWords]; b3 = p3[kTbRowWords]; }
+    if (A) {
+      const float hv = hA[pw];
+      *p0 = fmaf(w0, hv, a0); *p1 = fmaf(w1, hv, a1); *p2 = fmaf(w2, hv, a2); *p3 = fmaf(w3, hv, a3);
+    }
+    if (B) {
+      const float hv = hB[pw];
+      p0[kTbRowWords] = fmaf(w0, hv, b0); p1[kTbRowWords] = fmaf(w1, hv, b1);
+      p2[kTbRowWords] = fmaf(w2, hv, b2); p3[kTbRowWords] = fmaf(w3, hv, b3);
+    }
   }
 }
 
@@ -518,31 +540,38 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
   }
   __syncthreads();
   if (warp >= kTbWarps) {
+    pdl_wait();                     // the planner's lists and tables are complete
     tb_producer(d, c, w, gout, stages, ctl, lane, warp - kTbWarps);
     return;
   }
   // ================================= consumer warps ====================================
-  // Warp w owns tile row w for the whole kernel (fixed pitch, independent of the level's tile shape): it
-  // zeroes it once, accumulates every RoI of the item into it, and writes + re-zeroes it at the item's end.
+  // Warp w owns tile rows 2w and 2w+1 for the whole kernel (fixed pitch, independent of the level's tile shape): it
+  // zeroes them once, accumulates every RoI of the item into them, and writes + re-zeroes them at the item's end.
   // No barrier ever: the only coupling between warps is the depth of the message ring.
-  float* trow = tile + (size_t)(warp < c.max_rows ? warp : 0) * kTbRowWords;   // warps >= max_rows never own a row
-  if (warp < c.max_rows)
-    for (int i = lane; i < kTbRowWords; i += 32) trow[i] = 0.0f;
+  const int row0 = kTbR * warp;
+  float* trow = tile + (size_t)(row0 < c.max_rows ? row0 : 0) * kTbRowWords;     // rows >= max_rows are never owned
+  for (int r = 0; r < kTbR; ++r)
+    if (row0 + r < c.max_rows)
+      for (int i = lane; i < kTbRowWords; i += 32) trow[r * kTbRowWords + i] = 0.0f;
   __syncwarp();
+  pdl_wait();                       // (consumers store to the gradient maps: everything before this launch is complete)
+  pdl_launch_dependents();
   int s = 0;
   uint32_t par = 0;
-  bool have = false, touched = false;    // touched: some RoI of the item reached this warp's row
+  bool have = false, touchedA = false, touchedB = false;    // touched: some RoI of the item reached the row
   int lvl = 0, img = 0, c0 = 0, ty0 = 0, tx0 = 0, th = 0, tw = 0, H = 0, W = 0;
-  auto write_row = [&](bool zeros) {
-    const int gy = ty0 + warp;
-    if (warp >= th || gy >= H) return;
+  auto write_row = [&](int r, bool zeros) {
+    const int row = row0 + r;
+    const int gy = ty0 + row;
+    if (row >= th || gy >= H) return;
+    float* tr = trow + r * kTbRowWords;
     const int twe = min(tw, W - tx0);
     const size_t plane = (size_t)H * W;
     float* g0 = d.feat[lvl] + (((size_t)img * c.C + c0) * H + gy) * W + tx0;
     const bool acc = c.accumulate != 0;
     if (lane < twe) {                       // columns 0..31: lane = column, one channel per step
       float* gp = g0 + lane;
-      float* tp = trow + lane * kTbPix;
+      float* tp = tr + lane * kTbPix;
 #pragma unroll 8
       for (int ch = 0; ch < 32; ++ch) {
         float v = 0.0f;
@@ -555,7 +584,7 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
     const int x2 = 32 + (lane & 15), chb = (lane >> 4) * 16;   // columns 32..47: two channels (ch, ch+16) per step
     if (x2 < twe) {
       float* gp = g0 + (size_t)chb * plane + x2;
-      float* tp = trow + x2 * kTbPix + chb;
+      float* tp = tr + x2 * kTbPix + chb;
 #pragma unroll 8
       for (int ch = 0; ch < 16; ++ch) {
         float v = 0.0f;
@@ -580,15 +609,22 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
     const int hd = reinterpret_cast<const int*>(st)[0];
     const int kind = hd & 0xff;
     if (kind == kMsgPair) {
-      if (warp >= ((hd >> 8) & 0xff) && warp <= (hd >> 16)) {
-        touched = true;
+      const int ra = (hd >> 8) & 0xff, rb = hd >> 16;
+      const bool cA = row0 >= ra && row0 <= rb, cB = kTbR > 1 && row0 + 1 >= ra && row0 + 1 <= rb;
+      if (cA || cB) {
 #ifdef MXD_TB_PROF
         const long long _t = clock64();
 #endif
-        tb_row<PW>(reinterpret_cast<const float*>(st + c.off_g) + lane * c.bins,
-                   reinterpret_cast<const uint2*>(st + c.off_rt) + warp * 4,
-                   reinterpret_cast<const uint4*>(st + c.off_xt), reinterpret_cast<char*>(trow + lane),
-                   2.0f * c.inv_count);
+        const float* gl = reinterpret_cast<const float*>(st + c.off_g) + lane * c.bins;
+        const uint2* rt = reinterpret_cast<const uint2*>(st + c.off_rt) + row0 * 4;
+        const uint4* xt = reinterpret_cast<const uint4*>(st + c.off_xt);
+        char* rowp = reinterpret_cast<char*>(trow + lane);
+        float hA[PW], hB[PW];
+        const bool fA = cA && tb_h<PW>(gl, rt, hA), fB = cB && tb_h<PW>(gl, rt + 4, hB);
+        touchedA = touchedA || fA; touchedB = touchedB || fB;
+        if (fA && fB) tb_rmw2<PW, true, true>(hA, hB, xt, rowp, 2.0f * c.inv_count);
+        else if (fA) tb_rmw2<PW, true, false>(hA, hB, xt, rowp, 2.0f * c.inv_count);
+        else if (fB) tb_rmw2<PW, false, true>(hA, hB, xt, rowp, 2.0f * c.inv_count);
 #ifdef MXD_TB_PROF
         t_row += clock64() - _t;
 #endif
@@ -597,7 +633,7 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
 #ifdef MXD_TB_PROF
       const long long _t = clock64();
 #endif
-      if (have) write_row(!touched);     // an untouched row is still all zero: store zeros, skip the LDS / STS pass
+      if (have) { write_row(0, !touchedA); if (kTbR > 1) write_row(1, !touchedB); }     // an untouched row is still all zero: store zeros only
 #ifdef MXD_TB_PROF
       t_wr += clock64() - _t;
       if (kind == kMsgStop && lane == 0) {
@@ -607,13 +643,13 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
         atomicAdd(reinterpret_cast<unsigned long long*>(w.hdr + 26), (unsigned long long)(clock64() - t_call));
       }
 #endif
-      have = false; touched = false;
+      have = false; touchedA = touchedB = false;
       if (kind == kMsgStop) break;
       const int4 h1 = reinterpret_cast<const int4*>(st)[1];
       lvl = h1.x; img = h1.y; c0 = h1.z; ty0 = h1.w & 0xffff; tx0 = h1.w >> 16;
       th = c.lv[lvl].th; tw = c.lv[lvl].tw; H = c.lv[lvl].H; W = c.lv[lvl].W;
       if (kind == kMsgBegin) have = true;
-      else write_row(true);
+      else { write_row(0, true); if (kTbR > 1) write_row(1, true); }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&ctl->empty[s]);
@@ -625,6 +661,7 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
 __global__ void __launch_bounds__(256) tile_bwd_fallback_kernel(FpnDesc d, TCfg c, TWs w,
                                                                  const float* __restrict__ rois,
                                                                  const int* __restrict__ levels, float* gout) {
+  pdl_wait();                       // every tile is in HBM
   const int n_fb = w.hdr[1];
   const int chunks = (c.C + 31) / 32;
   for (int i = blockIdx.x; i < n_fb * chunks; i += gridDim.x) {
@@ -662,10 +699,10 @@ int tile_backward(const FpnDesc& d, const float* rois, const int* levels, const 
   MXD_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t zbytes = (size_t)((char*)w.start - (char*)w.hdr);    // hdr, cnt, cursor
   MXD_CUDA_OK(cudaMemsetAsync(w.hdr, 0, zbytes, st));
-  if (PH == 7) tplan_rois_kernel<7><<<(R * 32 + 255) / 256, 256, 0, st>>>(d, c, w, rois, levels, R);
-  else tplan_rois_kernel<14><<<(R * 32 + 255) / 256, 256, 0, st>>>(d, c, w, rois, levels, R);
+  if (PH == 7) MXD_CUDA_OK(launch_pdl(tplan_rois_kernel<7>, dim3((R * 32 + 255) / 256), dim3(256), 0, st, d, c, w, rois, levels, R));
+  else MXD_CUDA_OK(launch_pdl(tplan_rois_kernel<14>, dim3((R * 32 + 255) / 256), dim3(256), 0, st, d, c, w, rois, levels, R));
   MXD_POST_LAUNCH("roi_align_tplan_rois");
-  tplan_group_kernel<<<1, 1024, 0, st>>>(c, w, R);
+  MXD_CUDA_OK(launch_pdl(tplan_group_kernel, dim3(1), dim3(1024), 0, st, c, w, R));
   MXD_POST_LAUNCH("roi_align_tplan_group");
   static unsigned long long seen = 0;
   DeviceOnce once_seen(&seen);
@@ -673,10 +710,10 @@ int tile_backward(const FpnDesc& d, const float* rois, const int* levels, const 
     MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_tile_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem));
     MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_tile_bwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem));
   }
-  if (PW == 7) roi_align_tile_bwd_kernel<7><<<sms, kTbThreads, c.smem_bytes, st>>>(d, c, w, gout);
-  else roi_align_tile_bwd_kernel<14><<<sms, kTbThreads, c.smem_bytes, st>>>(d, c, w, gout);
+  if (PW == 7) MXD_CUDA_OK(launch_pdl(roi_align_tile_bwd_kernel<7>, dim3(sms), dim3(kTbThreads), (size_t)c.smem_bytes, st, d, c, w, gout));
+  else MXD_CUDA_OK(launch_pdl(roi_align_tile_bwd_kernel<14>, dim3(sms), dim3(kTbThreads), (size_t)c.smem_bytes, st, d, c, w, gout));
   MXD_POST_LAUNCH("roi_align_tile_bwd");
-  tile_bwd_fallback_kernel<<<2 * sms, 256, 0, st>>>(d, c, w, rois, levels, const_cast<float*>(gout));
+  MXD_CUDA_OK(launch_pdl(tile_bwd_fallback_kernel, dim3(2 * sms), dim3(256), 0, st, d, c, w, rois, levels, const_cast<float*>(gout)));
   MXD_POST_LAUNCH("roi_align_tile_bwd_fallback");
   *handled = 1;
   return MXD_OK;
