@@ -199,6 +199,18 @@ int mxd_pack_targets(const DLTensor* anchors, const DLTensor* assigned, const DL
                      float pos_weight, DLTensor* labels, DLTensor* label_weights, DLTensor* bbox_targets,
                      DLTensor* bbox_weights, void* stream);
 
+/* ---- N4  mask targets / mask paste  (SURVEY.md 8(f) "next" row N4: mxdetection/core/mask and models/mask_heads,
+ *      /root/reference/README.md:18,30; mask_target / FCNMaskHead.get_seg_masks of mmdet 0.5).
+ *      Target: gt_masks (G,H,W) u8, proposals (P,>=4) f32 image coords, gt_inds (P) i32 -> target (P,S,S), u8
+ *      [RoIAlign(mask, roi, S, scale 1, sample_ratio) >= thr] or f32 (the RoIAlign values); Spec A in strict fp32 on
+ *      the mask bytes, bit-exact.  Paste: mask_pred (n,C,S,S) or (n,S,S) f32 probabilities, labels (n) i32 or NULL
+ *      (class c reads channel c+1), det_bboxes (n,>=4) -> im_masks (n,img_h,img_w) u8; box = trunc(bbox /
+ *      scale_factor), half-pixel bilinear resize of the S x S map to the box, > thr (Spec N4).            */
+int mxd_mask_target(const DLTensor* gt_masks, const DLTensor* proposals, const DLTensor* gt_inds,
+                    DLTensor* target, int mask_size, int sample_ratio, float thr, void* stream);
+int mxd_paste_masks(const DLTensor* mask_pred, const DLTensor* labels, const DLTensor* det_bboxes,
+                    DLTensor* im_masks, float scale_factor, float thr, void* stream);
+
 /* ---- F1/F2  delta encode / decode + clip  (mxdetection/core/bbox,
  *      /root/reference/README.md:17; bbox2delta / delta2bbox of mmdet 0.5;
  *      Spec F).  means/stds: host float[4].  exp/log correctly rounded fp32.   */

@@ -186,6 +186,8 @@ _SIG = {
     "mxd_rpn_proposals_dims": [POINTER(RpnConfig), POINTER(c_int), POINTER(c_int)],
     "mxd_rpn_proposals": [_P, _P, _P, POINTER(RpnConfig), _P, _P, _P, c_size_t, _P],
     "mxd_rpn_proposals_stages": [POINTER(RpnConfig), c_int, _P, c_size_t, _P, _P, _P, _P, _P],
+    "mxd_mask_target": [_P, _P, _P, _P, c_int, c_int, c_float, _P],
+    "mxd_paste_masks": [_P, _P, _P, _P, c_float, c_float, _P],
     "mxd_pack_detections": [_P, _P, c_int, _P, _P],
     "mxd_copy2d_async": [_P, c_size_t, _P, c_size_t, c_size_t, c_size_t, c_int, _P],
     "mxd_multi_proposal_workspace_bytes": [c_int, c_int, c_int, c_int, c_int, c_int],

@@ -15,7 +15,7 @@ INC = os.path.join(os.path.dirname(HERE), "include")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libmxdet_sm100.so")
 SOURCES = ["abi_common.cu", "roi_align.cu", "roi_align_plane.cu", "roi_align_ring.cu", "roi_align_tile_bwd.cu", "topk.cu", "nms.cu", "anchors.cu", "assign.cu",
-           "codec.cu", "proposals.cu", "multi_proposal.cu", "targets.cu"]
+           "codec.cu", "proposals.cu", "multi_proposal.cu", "targets.cu", "mask.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I", INC] + os.environ.get("NVCC_EXTRA", "").split()      # e.g. -DMXD_RING_PROF

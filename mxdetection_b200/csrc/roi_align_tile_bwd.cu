@@ -31,9 +31,21 @@ namespace mxd {
 #ifndef MXD_TB_R
 #define MXD_TB_R 1
 #endif
+#ifndef MXD_TB_CTAS          // CTAs per SM (1: one 25-row tile + 9 stages; 2: two independent 12-row pipelines)
+#define MXD_TB_CTAS 1
+#endif
+#ifndef MXD_TB_ROWS
+#define MXD_TB_ROWS (MXD_TB_CTAS == 1 ? 25 : 12)
+#endif
+#ifndef MXD_TB_STAGES
+#define MXD_TB_STAGES (MXD_TB_CTAS == 1 ? 9 : 4)
+#endif
+#ifndef MXD_TB_PRODUCERS
+#define MXD_TB_PRODUCERS (MXD_TB_CTAS == 1 ? 4 : 2)
+#endif
 constexpr int kTbR = MXD_TB_R;                     // tile rows per consumer warp (1; 2 measured 5 % slower: fewer, fatter warps)
-constexpr int kTbWarps = (25 + kTbR - 1) / kTbR;   // consumer warps; warp w owns tile rows R*w .. R*w+R-1 (a tile has <= 25 rows)
-constexpr int kTbProducers = 4;                    // producer warps: message m is built by producer m mod 4 (one warp needs
+constexpr int kTbWarps = (MXD_TB_ROWS + kTbR - 1) / kTbR;   // consumer warps; warp w owns tile rows R*w .. R*w+R-1 (a tile has <= 25 rows)
+constexpr int kTbProducers = MXD_TB_PRODUCERS;                    // producer warps: message m is built by producer m mod 4 (one warp needs
                                                    // ~1500 cycles per message - two bulk copies, a barrier wait, the packed
                                                    // bins - and left the consumers waiting 30 % of the time)
 constexpr int kTbThreads = (kTbWarps + kTbProducers) * 32;
@@ -45,7 +57,7 @@ constexpr int kTbMaxTh = kTbR * kTbWarps;
 constexpr int kTbMaxTw = 48;
 constexpr int kTbRowWords = (kTbMaxTw + 1) * kTbPix;   // fixed row pitch: 48 columns + the trash column
 constexpr int kTbTrash = kTbMaxTw * kTbPix * 4;        // byte offset of the trash pixel inside a row
-constexpr int kTbSmem = 227 * 1024;
+constexpr int kTbSmem = MXD_TB_CTAS == 1 ? 227 * 1024 : 113 * 1024;
 constexpr int kTbCtlBytes = 384;                   // TbCtl
 
 enum { kMsgPair = 0, kMsgBegin = 1, kMsgZero = 2, kMsgStop = 3 };
@@ -104,7 +116,7 @@ static bool make_tcfg(int N, int C, int L, const int* Hs, const int* Ws, int PH,
   c->off_rt = (int)align_up((size_t)c->off_xt + PW * 16, 32);
   c->off_g = c->off_rt + kTbMaxTh * 32;
   c->stage_bytes = (int)align_up((size_t)c->off_g + 32 * c->bins * 4, 128);
-  c->n_stages = PW == 7 ? 9 : 4;                    // 7.5 KB / 26 KB of grad_out per stage
+  c->n_stages = PW == 7 ? MXD_TB_STAGES : (MXD_TB_CTAS == 1 ? 4 : 2);   // 7.5 KB / 26 KB of grad_out per stage
   c->tile_bytes = (kTbSmem - c->n_stages * c->stage_bytes - kTbCtlBytes) & ~15;
   const int max_rows = c->tile_bytes / (kTbRowWords * 4);
   c->max_rows = max_rows;
@@ -523,7 +535,7 @@ __device__ __forceinline__ void tb_rmw2(const float (&hA)[PW], const float (&hB)
 }
 
 template <int PW>
-__global__ void __launch_bounds__(kTbThreads, 1)
+__global__ void __launch_bounds__(kTbThreads, MXD_TB_CTAS)
 roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_constant__ TCfg c, TWs w,
                           const float* __restrict__ gout) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -710,8 +722,8 @@ int tile_backward(const FpnDesc& d, const float* rois, const int* levels, const 
     MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_tile_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem));
     MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_tile_bwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem));
   }
-  if (PW == 7) MXD_CUDA_OK(launch_pdl(roi_align_tile_bwd_kernel<7>, dim3(sms), dim3(kTbThreads), (size_t)c.smem_bytes, st, d, c, w, gout));
-  else MXD_CUDA_OK(launch_pdl(roi_align_tile_bwd_kernel<14>, dim3(sms), dim3(kTbThreads), (size_t)c.smem_bytes, st, d, c, w, gout));
+  if (PW == 7) MXD_CUDA_OK(launch_pdl(roi_align_tile_bwd_kernel<7>, dim3(sms * MXD_TB_CTAS), dim3(kTbThreads), (size_t)c.smem_bytes, st, d, c, w, gout));
+  else MXD_CUDA_OK(launch_pdl(roi_align_tile_bwd_kernel<14>, dim3(sms * MXD_TB_CTAS), dim3(kTbThreads), (size_t)c.smem_bytes, st, d, c, w, gout));
   MXD_POST_LAUNCH("roi_align_tile_bwd");
   MXD_CUDA_OK(launch_pdl(tile_bwd_fallback_kernel, dim3(2 * sms), dim3(256), 0, st, d, c, w, rois, levels, const_cast<float*>(gout)));
   MXD_POST_LAUNCH("roi_align_tile_bwd_fallback");

@@ -64,7 +64,47 @@ def get_det_bboxes(rois, cls_score, bbox_pred, img_shape, scale_factor=1.0, scor
     return multiclass_nms(b, cls_score, score_thr, iou_thr, max_per_img)
 
 
-def mask_target(pos_proposals, pos_gt_inds, gt_masks, mask_size=28, sample_ratio=2):
+def mask_target(pos_proposals, pos_gt_inds, gt_masks, mask_size=28, sample_ratio=2, thr=0.5):
     data = np.asarray(gt_masks, F)[:, None]
     rois = np.concatenate([np.asarray(pos_gt_inds, F)[:, None], np.asarray(pos_proposals, F)[:, :4]], 1)
-    return (roi_align_forward(data, rois, (mask_size, mask_size), 1.0, sample_ratio)[:, 0] >= F(0.5)).astype(np.uint8)
+    return (roi_align_forward(data, rois, (mask_size, mask_size), 1.0, sample_ratio)[:, 0] >= F(thr)).astype(np.uint8)
+
+
+def paste_masks(mask_pred, det_bboxes, img_shape, det_labels=None, scale_factor=1.0, thr=0.5):
+    """Spec N4 (mask paste; FCNMaskHead.get_seg_masks of mmdet 0.5 with the resize restated): per detection the integer
+    box x1i = trunc(x1 / scale), w = max(trunc(x2 / scale) - x1i + 1, 1) (same in y); canvas pixel (x, y) inside it samples the
+    S x S probability map at s = (d + 0.5) * (S / ext) - 0.5 (half-pixel convention; s < 0 -> index 0, s >= S-1 -> index S-1,
+    fraction 0 at both borders); top = m00 * (1 - lx) + m01 * lx, bot likewise, v = top * (1 - ly) + bot * ly, strict fp32;
+    pixel = v > thr.  mask_pred (n,C,S,S) with labels (class c reads channel c + 1) or (n,S,S)."""
+    mp = np.asarray(mask_pred, F)
+    n = mp.shape[0]
+    S = mp.shape[-1]
+    H, W = int(img_shape[0]), int(img_shape[1])
+    out = np.zeros((n, H, W), np.uint8)
+    sc = F(scale_factor)
+
+    def axis(ext):
+        d = np.arange(ext, dtype=F)
+        s = ((d + F(0.5)) * (F(S) / F(ext))).astype(F) - F(0.5)
+        lo = np.floor(s).astype(np.int64)
+        fr = (s - lo.astype(F)).astype(F)
+        under = lo < 0; over = lo >= S - 1
+        lo = np.where(under, 0, np.where(over, S - 1, lo))
+        fr = np.where(under | over, F(0), fr).astype(F)
+        return lo, np.minimum(lo + 1, S - 1), fr
+
+    for i in range(n):
+        bb = (np.asarray(det_bboxes[i, :4], F) / sc).astype(F)
+        x1, y1, x2, y2 = [int(v) for v in bb]                      # truncation toward zero
+        w = max(x2 - x1 + 1, 1); h = max(y2 - y1 + 1, 1)
+        m = mp[i] if mp.ndim == 3 else mp[i, int(det_labels[i]) + 1]
+        xa, xb, lx = axis(w); ya, yb, ly = axis(h)
+        hx = (F(1) - lx).astype(F); hy = (F(1) - ly).astype(F)
+        top = ((m[ya][:, xa] * hx[None, :]).astype(F) + (m[ya][:, xb] * lx[None, :]).astype(F)).astype(F)
+        bot = ((m[yb][:, xa] * hx[None, :]).astype(F) + (m[yb][:, xb] * lx[None, :]).astype(F)).astype(F)
+        v = ((top * hy[:, None]).astype(F) + (bot * ly[:, None]).astype(F)).astype(F)
+        box = (v > F(thr)).astype(np.uint8)
+        ys = slice(max(y1, 0), min(y1 + h, H)); xs = slice(max(x1, 0), min(x1 + w, W))
+        if ys.stop > ys.start and xs.stop > xs.start:
+            out[i, ys, xs] = box[ys.start - y1: ys.stop - y1, xs.start - x1: xs.stop - x1]
+    return out

@@ -68,6 +68,6 @@ print("N3 MultiProposal 2 x %d anchors, 6000 -> 300: %.3f ms" % (H * W * A, time
 G = 20
 masks = (rng.random((G, 800, 1344)) > 0.5).astype(np.uint8)
 props = syn.gt_boxes(rng, 800, 1344, 128)
-inds = rng.integers(0, G, 128).astype(np.int64)
+inds = rng.integers(0, G, 128).astype(np.int32)
 tm, tpz, tix = T(masks), T(props), T(inds)
 print("N4 mask_target 128 RoIs x 28x28 from 20 masks: %.3f ms" % timed(lambda: mask_target(tpz, tix, tm, 28)))

@@ -842,7 +842,9 @@ def test_multiclass_nms_and_det_bboxes_n2():
     assert int(n2.item()) == 0 and np.all(N(l2) == -1)
 
 
-def test_mask_target_n4():
+def test_mask_target_n4_bit_exact():
+    """uint8 masks read directly by mxd_mask_target, Spec A in strict fp32: targets AND the fp32 RoIAlign values are
+    bit-exact against the oracle (RoIs inside, across and outside the mask, degenerate, bad GT index)."""
     from mxdetection_b200.core.mask import mask_target
     rng = np.random.default_rng(8)
     G, H, W = 5, 96, 128
@@ -850,11 +852,41 @@ def test_mask_target_n4():
     for g in range(G):
         y, x = np.ogrid[:H, :W]
         masks[g] = ((y - rng.uniform(20, 70)) ** 2 / rng.uniform(100, 900) + (x - rng.uniform(30, 100)) ** 2 / rng.uniform(100, 1600)) <= 1
-    props = syn.gt_boxes(rng, H, W, 40)
-    inds = rng.integers(0, G, 40)
-    got = N(mask_target(T(props), T(inds.astype(np.int64)), T(masks), 28))
-    ref = oracle.targets.mask_target(props, inds, masks, 28)
-    assert got.shape == (40, 28, 28) and np.mean(got != ref) <= 1e-3        # >= 0.5 boundary pixels may flip by 1 ulp
+    props = syn.gt_boxes(rng, H, W, 60)
+    props[:4] = [[-30, -20, 40, 50], [100, 80, 140, 110], [50, 50, 50, 50], [10.25, 3.5, 90.75, 95.9]]
+    inds = rng.integers(0, G, 60).astype(np.int32)
+    inds[7] = -1; inds[8] = G                                        # out of range -> zeros
+    for S, sr in ((28, 2), (14, 2), (28, -1), (7, 3)):
+        got = N(mask_target(T(props), T(inds), T(masks), S, sample_ratio=sr))
+        ref = oracle.targets.mask_target(props, inds, masks, S, sr)
+        assert got.shape == (60, S, S) and np.array_equal(got, ref), (S, sr)
+        raw = N(mask_target(T(props), T(inds), T(masks), S, sample_ratio=sr, binarize=False))
+        data = masks.astype(F)[:, None]
+        rois = np.concatenate([inds.astype(F)[:, None], props[:, :4]], 1)
+        assert np.array_equal(raw, oracle.roi_align_forward(data, rois, (S, S), 1.0, sr)[:, 0])
+    assert np.all(got[7] == 0) and np.all(got[8] == 0) and got.sum() > 0
+
+
+def test_mask_paste_n4_bit_exact():
+    """mxd_paste_masks (FCNMaskHead.get_seg_masks): class-indexed S x S probabilities -> image-size uint8 masks."""
+    from mxdetection_b200.models.mask_heads import get_seg_masks
+    from mxdetection_b200.core.mask import paste_masks
+    rng = np.random.default_rng(21)
+    n, C, S, H, W = 12, 5, 28, 150, 203
+    pred = rng.uniform(0, 1, (n, C, S, S)).astype(F)
+    pred[0, :, :, :] = 0.5                                          # exactly at the threshold: strict > keeps it out
+    boxes = np.concatenate([syn.gt_boxes(rng, H, W, n), rng.uniform(0, 1, (n, 1)).astype(F)], 1).astype(F)
+    boxes[1, :4] = [-20, -10, 60, 70]                               # crosses the image border
+    boxes[2, :4] = [30, 40, 30, 40]                                 # one pixel
+    boxes[3, :4] = [W - 10, H - 10, W + 30, H + 30]
+    labels = rng.integers(0, C - 1, n).astype(np.int32)
+    for scale in (1.0, 1.6):
+        got = N(get_seg_masks(T(pred), T(boxes), T(labels), (H, W, 3), scale_factor=scale))
+        ref = oracle.targets.paste_masks(pred, boxes, (H, W), labels, scale)
+        assert got.shape == (n, H, W) and np.array_equal(got, ref), scale
+    assert got[0].sum() == 0 and ref.sum() > 0
+    single = N(paste_masks(T(pred[:, 1].copy()), T(boxes), (H, W)))
+    assert np.array_equal(single, oracle.targets.paste_masks(pred[:, 1], boxes, (H, W)))
 
 
 def test_empty_and_one_sided_inputs():

@@ -288,6 +288,24 @@ def test_next_row_oracles_hand_cases():
 
 
 # ------------------------------------------------ size-independent properties of the oracle ----
+def test_mask_paste_oracle_hand_cases():
+    """Spec N4 paste: a box of exactly S x S pixels reproduces the thresholded map (sample positions hit the centres),
+    a constant map stays constant at any size, boxes crossing the border are cropped, scale_factor divides the box."""
+    rng = np.random.default_rng(2)
+    S = 7
+    m = rng.uniform(0, 1, (1, S, S)).astype(F)
+    box = np.array([[10, 20, 10 + S - 1, 20 + S - 1]], F)
+    out = oracle.targets.paste_masks(m, box, (40, 50))
+    assert np.array_equal(out[0, 20:20 + S, 10:10 + S], (m[0] > 0.5).astype(np.uint8)) and out.sum() == (m[0] > 0.5).sum()
+    ones = np.full((1, S, S), 0.75, F)
+    big = oracle.targets.paste_masks(ones, np.array([[-5, -5, 30, 12]], F), (20, 25))
+    assert big[0, :13, :25].all() and big[0, 13:].sum() == 0          # cropped at the border, 1 everywhere inside
+    half = oracle.targets.paste_masks(ones, np.array([[20, 20, 39, 39]], F), (40, 40), scale_factor=2.0)
+    assert half[0, 10:20, 10:20].all() and half.sum() == 100          # box / 2 = [10, 19]
+    lab = oracle.targets.paste_masks(np.stack([np.zeros((S, S), F), ones[0]])[None], box, (40, 50), np.array([0], np.int32))
+    assert lab.sum() == S * S                                          # label 0 reads channel 1
+
+
 def test_oracle_properties_adjoint_linearity_idempotence():
     """The properties the GPU tests lean on at full size, checked on the oracle itself: RoIAlign backward is the
     adjoint of forward (<fwd(x), g> == <x, bwd(g)>), forward is linear in the features, NMS of its own survivors
