@@ -41,7 +41,7 @@ namespace mxd {
 #define MXD_TB_STAGES (MXD_TB_CTAS == 1 ? 9 : 4)
 #endif
 #ifndef MXD_TB_PRODUCERS
-#define MXD_TB_PRODUCERS (MXD_TB_CTAS == 1 ? 4 : 2)
+#define MXD_TB_PRODUCERS (MXD_TB_CTAS == 1 ? 3 : 2)       /* 25 + 3 warps = 896 threads: 72 registers per thread */
 #endif
 constexpr int kTbR = MXD_TB_R;                     // tile rows per consumer warp (1; 2 measured 5 % slower: fewer, fatter warps)
 constexpr int kTbWarps = (MXD_TB_ROWS + kTbR - 1) / kTbR;   // consumer warps; warp w owns tile rows R*w .. R*w+R-1 (a tile has <= 25 rows)
@@ -572,15 +572,42 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
   uint32_t par = 0;
   bool have = false, touchedA = false, touchedB = false;    // touched: some RoI of the item reached the row
   int lvl = 0, img = 0, c0 = 0, ty0 = 0, tx0 = 0, th = 0, tw = 0, H = 0, W = 0;
-  auto write_row = [&](int r, bool zeros) {
+  const bool acc = c.accumulate != 0;
+  // req=add: the first RoI that reaches a row loads the row's current gradient into the tile (coalesced, 8 loads in
+  // flight per lane), so the write-out stays a plain store and untouched rows cost nothing.  (Adding on the way out -
+  // a dependent global load per element inside the store loop - measured 1.03 ms against 0.41 ms for req=write.)
+  auto load_row = [&](int r) {
     const int row = row0 + r;
     const int gy = ty0 + row;
     if (row >= th || gy >= H) return;
     float* tr = trow + r * kTbRowWords;
     const int twe = min(tw, W - tx0);
     const size_t plane = (size_t)H * W;
+    const float* g0 = d.feat[lvl] + (((size_t)img * c.C + c0) * H + gy) * W + tx0;
+    if (lane < twe) {
+      const float* gp = g0 + lane;
+      float* tp = tr + lane * kTbPix;
+#pragma unroll 8
+      for (int ch = 0; ch < 32; ++ch) { tp[ch] = __ldg(gp); gp += plane; }
+    }
+    const int x2 = 32 + (lane & 15), chb = (lane >> 4) * 16;
+    if (x2 < twe) {
+      const float* gp = g0 + (size_t)chb * plane + x2;
+      float* tp = tr + x2 * kTbPix + chb;
+#pragma unroll 8
+      for (int ch = 0; ch < 16; ++ch) { tp[ch] = __ldg(gp); gp += plane; }
+    }
+    __syncwarp();
+  };
+  auto write_row = [&](int r, bool zeros) {
+    const int row = row0 + r;
+    const int gy = ty0 + row;
+    if (row >= th || gy >= H) return;
+    if (acc && zeros) return;               // req=add: nothing was added to this row
+    float* tr = trow + r * kTbRowWords;
+    const int twe = min(tw, W - tx0);
+    const size_t plane = (size_t)H * W;
     float* g0 = d.feat[lvl] + (((size_t)img * c.C + c0) * H + gy) * W + tx0;
-    const bool acc = c.accumulate != 0;
     if (lane < twe) {                       // columns 0..31: lane = column, one channel per step
       float* gp = g0 + lane;
       float* tp = tr + lane * kTbPix;
@@ -588,7 +615,6 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
       for (int ch = 0; ch < 32; ++ch) {
         float v = 0.0f;
         if (!zeros) { v = tp[ch]; tp[ch] = 0.0f; }
-        if (acc) v += *gp;
         *gp = v;
         gp += plane;
       }
@@ -601,7 +627,6 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
       for (int ch = 0; ch < 16; ++ch) {
         float v = 0.0f;
         if (!zeros) { v = tp[ch]; tp[ch] = 0.0f; }
-        if (acc) v += *gp;
         *gp = v;
         gp += plane;
       }
@@ -631,12 +656,25 @@ roi_align_tile_bwd_kernel(const __grid_constant__ FpnDesc d, const __grid_consta
         const uint2* rt = reinterpret_cast<const uint2*>(st + c.off_rt) + row0 * 4;
         const uint4* xt = reinterpret_cast<const uint4*>(st + c.off_xt);
         char* rowp = reinterpret_cast<char*>(trow + lane);
-        float hA[PW], hB[PW];
-        const bool fA = cA && tb_h<PW>(gl, rt, hA), fB = cB && tb_h<PW>(gl, rt + 4, hB);
-        touchedA = touchedA || fA; touchedB = touchedB || fB;
-        if (fA && fB) tb_rmw2<PW, true, true>(hA, hB, xt, rowp, 2.0f * c.inv_count);
-        else if (fA) tb_rmw2<PW, true, false>(hA, hB, xt, rowp, 2.0f * c.inv_count);
-        else if (fB) tb_rmw2<PW, false, true>(hA, hB, xt, rowp, 2.0f * c.inv_count);
+        if constexpr (kTbR == 1) {
+          float hA[PW];
+          if (tb_h<PW>(gl, rt, hA)) {
+            if (acc && !touchedA) load_row(0);
+            touchedA = true;
+            tb_rmw2<PW, true, false>(hA, hA, xt, rowp, 2.0f * c.inv_count);
+          }
+        } else {
+          float hA[PW], hB[PW];
+          const bool fA = cA && tb_h<PW>(gl, rt, hA), fB = cB && tb_h<PW>(gl, rt + 4, hB);
+          if (acc) {
+            if (fA && !touchedA) load_row(0);
+            if (fB && !touchedB) load_row(1);
+          }
+          touchedA = touchedA || fA; touchedB = touchedB || fB;
+          if (fA && fB) tb_rmw2<PW, true, true>(hA, hB, xt, rowp, 2.0f * c.inv_count);
+          else if (fA) tb_rmw2<PW, true, false>(hA, hB, xt, rowp, 2.0f * c.inv_count);
+          else if (fB) tb_rmw2<PW, false, true>(hA, hB, xt, rowp, 2.0f * c.inv_count);
+        }
 #ifdef MXD_TB_PROF
         t_row += clock64() - _t;
 #endif
@@ -712,9 +750,12 @@ int tile_backward(const FpnDesc& d, const float* rois, const int* levels, const 
   const size_t zbytes = (size_t)((char*)w.start - (char*)w.hdr);    // hdr, cnt, cursor
   MXD_CUDA_OK(cudaMemsetAsync(w.hdr, 0, zbytes, st));
   if (PH == 7) MXD_CUDA_OK(launch_pdl(tplan_rois_kernel<7>, dim3((R * 32 + 255) / 256), dim3(256), 0, st, d, c, w, rois, levels, R));
-  else MXD_CUDA_OK(launch_pdl(tplan_rois_kernel<14>, dim3((R * 32 + 255) / 256), dim3(256), 0, st, d, c, w, rois, levels, R));
+  else MXD_CUDA_OK(launch_pdl_if(false, tplan_rois_kernel<14>, dim3((R * 32 + 255) / 256), dim3(256), 0, st, d, c, w, rois, levels, R));
   MXD_POST_LAUNCH("roi_align_tplan_rois");
-  MXD_CUDA_OK(launch_pdl(tplan_group_kernel, dim3(1), dim3(1024), 0, st, c, w, R));
+  // (the 14x14 chain measured 37 us SLOWER with programmatic launches - 0.419 vs 0.382 ms on BASELINE config 4a - and keeps
+  // plain stream order; the 7x7 chain gains 9 us)
+  const bool pdl = PW == 7;
+  MXD_CUDA_OK(launch_pdl_if(pdl, tplan_group_kernel, dim3(1), dim3(1024), 0, st, c, w, R));
   MXD_POST_LAUNCH("roi_align_tplan_group");
   static unsigned long long seen = 0;
   DeviceOnce once_seen(&seen);
@@ -723,9 +764,9 @@ int tile_backward(const FpnDesc& d, const float* rois, const int* levels, const 
     MXD_CUDA_OK(cudaFuncSetAttribute(roi_align_tile_bwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem));
   }
   if (PW == 7) MXD_CUDA_OK(launch_pdl(roi_align_tile_bwd_kernel<7>, dim3(sms * MXD_TB_CTAS), dim3(kTbThreads), (size_t)c.smem_bytes, st, d, c, w, gout));
-  else MXD_CUDA_OK(launch_pdl(roi_align_tile_bwd_kernel<14>, dim3(sms * MXD_TB_CTAS), dim3(kTbThreads), (size_t)c.smem_bytes, st, d, c, w, gout));
+  else MXD_CUDA_OK(launch_pdl_if(false, roi_align_tile_bwd_kernel<14>, dim3(sms * MXD_TB_CTAS), dim3(kTbThreads), (size_t)c.smem_bytes, st, d, c, w, gout));
   MXD_POST_LAUNCH("roi_align_tile_bwd");
-  MXD_CUDA_OK(launch_pdl(tile_bwd_fallback_kernel, dim3(2 * sms), dim3(256), 0, st, d, c, w, rois, levels, const_cast<float*>(gout)));
+  MXD_CUDA_OK(launch_pdl_if(pdl, tile_bwd_fallback_kernel, dim3(2 * sms), dim3(256), 0, st, d, c, w, rois, levels, const_cast<float*>(gout)));
   MXD_POST_LAUNCH("roi_align_tile_bwd_fallback");
   *handled = 1;
   return MXD_OK;
