@@ -34,7 +34,7 @@ def timed(fn, n=10):
 
 
 res = {}
-for name, sel in [("all", np.ones(len(lv), bool)), ("none", np.zeros(len(lv), bool))] + [("L%d" % l, lv == l) for l in range(4)]:
+for name, sel in [("all", np.ones(len(lv), bool)), ("none", np.zeros(len(lv), bool)), ("L123", lv > 0), ("L01", lv < 2), ("L23", lv >= 2)] + [("L%d" % l, lv == l) for l in range(4)]:
     rois = rois_all[torch.from_numpy(np.nonzero(sel)[0]).to(dev)].contiguous()
     gout = torch.randn((rois.shape[0], 256, 7, 7), device=dev)
     out = torch.empty_like(gout)
