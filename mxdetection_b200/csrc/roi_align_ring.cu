@@ -18,14 +18,16 @@
 //    the two fine FPN levels; here they carry 2 and 4, the coarse ones 8).
 //  * A consumer warp owns a (RoI, all cg channels) job: it expands the RoI's packed table ONCE into registers -
 //    14 row offsets and 28 tap weights, already multiplied by the lane's x weight - and then runs the channel
-//    loop as 28 LDS [R + UR] + 28 FFMA + a 16-instruction fold + 2 stores per (RoI, channel); lane = x tap as
-//    before (sample l>>1, low/high tap l&1), so one LDS reads the 28 taps of a sample row without bank conflicts.
-//    The lanes of a bin hold their bin rows in PERMUTED order (slot i = bin row i ^ (lane & 3)), which makes the
-//    transposing butterfly of the fold select-free.
+//    loop as 28 LDS [R + immediate] + 28 FFMA + a fold (6 shuffles) + 2 stores per (RoI, channel); lane = x tap
+//    (sample l>>1, low/high tap l&1), so one LDS reads the 28 taps of a sample row without bank conflicts.
+//    (Holding the bin rows in lane-PERMUTED slots makes the fold select-free but lets one LDS read four different
+//    rows: 26 M bank-conflict wavefronts, 0.39 ms - rejected.)
 //  * Small levels whose rows cannot be bulk-copied one by one (W*4 not a multiple of 16) run in "tall" mode:
 //    cg whole planes are one contiguous copy into one of two slots; same consumer code, same barriers.
-//  * Synchronisation: full[s] (transaction barriers, one per ring slot), empty[s] (every consumer warp releases
-//    every chunk once, after waiting for it, in order), and a small ring of unit descriptors.  No CTA barrier.
+//  * Synchronisation: full[q & 15] transaction barriers (fills are numbered absolutely: barrier q & 15, parity
+//    (q >> 4) & 1), one progress word per consumer warp (the global number of the job it is working on, published
+//    with st.release) that the producer polls to learn when a ring slot's rows are dead, and a small ring of unit
+//    descriptors.  Jobs are dealt round-robin by global job number across units.  No CTA barrier, no atomics.
 //  * RoIs that need more rows than the ring holds, sample outside the image or carry a bad batch index take the
 //    generic gather afterwards (same kernel, extra units).
 #include <cuda.h>
@@ -36,7 +38,7 @@
 namespace mxd {
 
 constexpr int kRgSmem = 227 * 1024;
-constexpr int kRgThreads = 640;                 // 23 consumer warps + 1 producer warp; <= 85 registers per thread
+constexpr int kRgThreads = 640;                 // 19 consumer warps + 1 producer warp; 96 registers per thread (768 / 1024 threads spill and are slower)
 constexpr int kRgWarps = kRgThreads / 32 - 1;
 constexpr int kRgSlotsMax = 16;                 // ring slots (mbarriers)
 constexpr int kRgDesc = 4;                      // unit-descriptor ring
