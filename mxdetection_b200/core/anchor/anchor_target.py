@@ -1,6 +1,6 @@
 """Anchor flags and anchor -> GT assignment (mmdet-0.5 anchor_target leaf
 functions; mxdetection/core/anchor, /root/reference/README.md:16).
-Sampling / target packing are SURVEY.md 8(f) N1 (next), not built here."""
+Sampling / target packing are native too: mxd_random_sample / mxd_pack_targets."""
 import torch
 
 from ... import _lib as L

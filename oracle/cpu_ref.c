@@ -6,7 +6,8 @@
  * only); the contract is mxnet 1.3.0 contrib ROIAlign / box_nms /
  * MultiProposal (/root/reference/README.md:37) in the module roles of
  * /root/reference/README.md:16-17,24,28,32.  Checked against oracle/ *.py files
- * (tests/test_c_oracle.py), which in turn is checked against torchvision CPU.
+ * (tests/test_oracle.py: C port vs NumPy restatement), which in turn are checked against
+ * torchvision CPU fixtures (tests/golden) and the independent routes of tests/test_cross_oracle.py.
  *
  * Parallelisation mirrors the reference stack: OpenMP over RoIs in RoIAlign
  * forward (as mxnet's roi_align.cc), serial backward (as mxnet's), OpenMP over
