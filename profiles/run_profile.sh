@@ -4,7 +4,7 @@
 set -u
 TAG=${1:-r1}
 OUT=gpurun_out
-SHORT="python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline --e2e-steps 1"
+SHORT="python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline --no-e2e"
 python bench.py --steps 10 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2>> $OUT/bench_$TAG.err; echo "ref rc=$?"
 $SHORT > $OUT/plain_$TAG.log 2>&1 && \
