@@ -167,3 +167,28 @@ def test_product_package_never_imports_the_oracle_and_has_no_cpu_path():
     # the C sources reference the oracle nowhere either
     for f in os.listdir(os.path.join(root, "csrc")):
         assert "oracle" not in open(os.path.join(root, "csrc", f)).read().lower(), f
+
+
+def test_integration_snippets_are_self_consistent():
+    """the code blocks parse, every free name they use is defined in the blocks (or is a builtin / the
+    mxnet import the maintainer's process already has), and every `lib.mxd_*` they call is a declared entry point."""
+    import ast
+    import builtins
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, re.S)
+    assert len(blocks) >= 2
+    tree = ast.parse("\n".join(blocks))
+    defined = set(dir(builtins)) | {"mx", "self"}
+    for node in ast.walk(tree):
+        if isinstance(node, (ast.FunctionDef, ast.ClassDef)):
+            defined.add(node.name)
+            if isinstance(node, ast.FunctionDef):
+                defined.update(a.arg for a in node.args.args + node.args.kwonlyargs)
+        elif isinstance(node, (ast.Import, ast.ImportFrom)):
+            defined.update((a.asname or a.name).split(".")[0] for a in node.names)
+        elif isinstance(node, ast.Name) and isinstance(node.ctx, ast.Store):
+            defined.add(node.id)
+    used = {n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
+    assert not (used - defined), "INTEGRATION.md uses undefined names: %s" % sorted(used - defined)
+    called = set(re.findall(r"lib\.(mxd_[a-z0-9_]+)", "\n".join(blocks)))
+    assert called and called <= set(declared_symbols()), sorted(called - set(declared_symbols()))
