@@ -84,7 +84,8 @@ struct TWs {
   int4* roihdr;    // [R][2]  {y0, Hf, x0, x1} {b, lvl, ok, ntiles}
   uint2* xtab;     // [R][tx] {column of the low tap (unclamped form), weight of the high tap}
   uint4* rowtab;   // [R][max_hf][2]  {first bin | nbins<<8, w0..w6}
-  int* pairs;      // [R * kTbMaxTiles]
+  int* pairs;      // [R * kTbMaxTiles]  per-tile RoI lists, ascending RoI index (deterministic summation order)
+  int* pairs_raw;  // [R * kTbMaxTiles]  the same lists in the order the grouping atomics happened to fill them
   size_t bytes;
 };
 
@@ -102,6 +103,7 @@ static TWs carve_tile(void* base, int R, int NT, int tx, int max_hf) {
   w.xtab = (uint2*)take(sizeof(uint2) * r1 * tx);
   w.rowtab = (uint4*)take(sizeof(uint4) * 2 * r1 * max_hf);
   w.pairs = (int*)take(sizeof(int) * r1 * kTbMaxTiles);
+  w.pairs_raw = (int*)take(sizeof(int) * r1 * kTbMaxTiles);
   w.bytes = off;
   return w;
 }
@@ -299,8 +301,59 @@ __global__ void __launch_bounds__(1024) tplan_group_kernel(TCfg c, TWs w, int R)
       for (int tx = txa; tx <= txb; ++tx) {
         const int t = h1.x * c.tiles_per_img + v.tile_base + ty * v.ntx + tx;
         const int pos = in_smem ? atomicAdd(&s_pos[t], 1) : w.start[t] + atomicAdd(&w.cursor[t], 1);
-        w.pairs[pos] = n;
+        w.pairs_raw[pos] = n;
       }
+  }
+}
+
+// Orders every tile's list by RoI index: the consumers add the RoIs of a tile in list order, so a list in atomic-
+// arrival order makes the gradient differ in the last bits from run to run.  One warp per tile: the ids are marked in
+// a 4096-bit shared-memory bitmap (window by window over the list's id range - one window when a tile's RoIs are
+// neighbours in the RoI array, as the RoIs of one image usually are) and read back in ascending order.
+__global__ void __launch_bounds__(256) tplan_sort_kernel(TCfg c, TWs w) {
+  __shared__ unsigned s_bm[8][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();                       // the raw lists are complete
+  pdl_launch_dependents();
+  unsigned* bm = s_bm[warp];
+  const int t = blockIdx.x * 8 + warp;
+  if (t >= c.NT) return;
+  const int cnt = w.cnt[t];
+  if (cnt == 0) return;
+  const int st = w.start[t];
+  int lo = 0x7fffffff, hi = -1;
+  for (int i = lane; i < cnt; i += 32) { const int id = w.pairs_raw[st + i]; lo = min(lo, id); hi = max(hi, id); }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  int wpos = st;
+  for (int base = lo; base <= hi; base += 4096) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bm[lane * 4 + k] = 0u;
+    __syncwarp();
+    for (int i = lane; i < cnt; i += 32) {
+      const unsigned r = (unsigned)(w.pairs_raw[st + i] - base);
+      if (r < 4096u) atomicOr(&bm[r >> 5], 1u << (r & 31));
+    }
+    __syncwarp();
+    unsigned wd[4];
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { wd[k] = bm[lane * 4 + k]; mine += __popc(wd[k]); }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    int off = wpos + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unsigned bits = wd[k];
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        w.pairs[off++] = base + (lane * 4 + k) * 32 + b;
+      }
+    }
+    wpos += __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
   }
 }
 
@@ -769,6 +822,8 @@ int tile_backward(const FpnDesc& d, const float* rois, const int* levels, const 
   const bool pdl = PW == 7;
   MXD_CUDA_OK(launch_pdl_if(pdl, tplan_group_kernel, dim3(1), dim3(1024), 0, st, c, w, R));
   MXD_POST_LAUNCH("roi_align_tplan_group");
+  MXD_CUDA_OK(launch_pdl_if(pdl, tplan_sort_kernel, dim3((c.NT + 7) / 8), dim3(256), 0, st, c, w));
+  MXD_POST_LAUNCH("roi_align_tplan_sort");
   static unsigned long long seen = 0;
   DeviceOnce once_seen(&seen);
   if (once_seen.first()) {

@@ -270,6 +270,34 @@ def test_fpn_roi_stage_cfg3_benchmarked_shape_all_8_images():
         assert close(N(a), 2 * b, 1e-4)
 
 
+def test_fpn_roi_stage_is_deterministic_under_repetition():
+    """Neither RoIAlign kernel of the benchmarked shape uses atomics (the RoIs of config 3 are clipped to the image, so the
+    RED fallback list is empty): 40 back-to-back forward / backward launches on buffers that are re-used while the next
+    launch's planners already run (programmatic dependent launch) must be BIT-identical.  A race between the producer
+    warp, the progress words and the consumer warps of the persistent kernels would show up here as a flipped bit."""
+    from mxdetection_b200.ops import roi_align_fpn_forward, roi_align_fpn_backward
+    d = syn.cfg3(batch=8, with_features=False)
+    shapes = [(8, 256, h, w) for h, w in d["feat_shapes"]]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    feats = [torch.randn(s, device="cuda", generator=g) for s in shapes]
+    rois = T(d["rois"])
+    gout = torch.randn((rois.shape[0], 256, 7, 7), device="cuda", generator=g)
+    out0 = roi_align_fpn_forward(feats, rois, (7, 7), d["scales"], 2).clone()
+    out = torch.empty_like(out0)
+    for _ in range(40):
+        out.fill_(float("nan"))
+        roi_align_fpn_forward(feats, rois, (7, 7), d["scales"], 2, out=out)
+        assert torch.equal(out, out0)
+    del feats
+    g0 = [t.clone() for t in roi_align_fpn_backward(gout, rois, shapes, (7, 7), d["scales"], 2)]
+    grads = [torch.empty_like(t) for t in g0]
+    for _ in range(40):
+        for t in grads:
+            t.fill_(float("nan"))
+        roi_align_fpn_backward(gout, rois, shapes, (7, 7), d["scales"], 2, grad_feats=grads)
+        assert all(torch.equal(a, b) for a, b in zip(grads, g0))
+
+
 @pytest.mark.parametrize("W,C", [(400, 20), (512, 8), (520, 8), (352, 6), (356, 4)])
 def test_roi_align_ring_wide_maps_and_class_edges(W, C, roi_path):
     """Row pitch classes of the ring forward: 352 / 704 / 1408 / 2048 bytes.  W = 352 is the widest 2-channel class,
