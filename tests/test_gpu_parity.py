@@ -789,6 +789,32 @@ def test_rpn_proposals_cfg2_full_size():
     assert np.all(props[:, :-1, 4] >= props[:, 1:, 4])           # sortedness of the truncated output
 
 
+def test_rpn_proposals_and_assigner_repeatable_bit_for_bit():
+    """The latency-bound stages use shared-memory atomics for compaction and per-GT maxima; their RESULTS must not depend
+    on arrival order: 25 back-to-back launches of the config-5-shard proposal stage (8 images, 4-CTA clusters) and of
+    the assigner are bit-identical (a race in the cluster top-k, the NMS ring or pass 1 / pass 2 would show up here)."""
+    from mxdetection_b200.models.rpn_heads import ProposalConfig, RPNHead
+    from mxdetection_b200.core.bbox import MaxIoUAssigner
+    d = syn.rpn_inputs(77, 8, 800, 1344)
+    sc = [T(x) for x in d["scores"]]; dl = [T(x) for x in d["deltas"]]; shp = T(d["img_shapes"])
+    head, cfg = RPNHead(), ProposalConfig(nms_pre=2000, nms_post=1000, max_num=1000, nms_thr=0.7)
+    p0, n0 = head.get_proposals(sc, dl, d["feat_shapes"], shp, cfg)
+    p0, n0 = p0.clone(), n0.clone()
+    for _ in range(25):
+        p, n = head.get_proposals(sc, dl, d["feat_shapes"], shp, cfg)
+        assert torch.equal(n, n0) and torch.equal(p, p0)
+    rng = np.random.default_rng(4)
+    base = [oracle.gen_base_anchors(s, [8], [0.5, 1, 2]) for s in d["strides"]]
+    anc = np.concatenate([oracle.grid_anchors(b, fh, fw, st) for b, (fh, fw), st in zip(base, d["feat_shapes"], d["strides"])])
+    gts = syn.gt_boxes(rng, 800, 1344, 100)
+    asg = MaxIoUAssigner(0.7, 0.3, 0.3)
+    a0 = asg.assign(T(anc), T(gts))
+    a0 = [t.clone() for t in (a0.gt_inds, a0.max_overlaps)]
+    for _ in range(25):
+        a = asg.assign(T(anc), T(gts))
+        assert torch.equal(a.gt_inds, a0[0]) and torch.equal(a.max_overlaps, a0[1])
+
+
 def test_rpn_proposals_stock_training_config_2000x5_levels():
     """The lineage's stock TRAINING proposal config: nms_pre = nms_post = max_num = 2000 on 5 levels - up to 10 000 kept
     candidates are merged per image (more than one 8192-entry sort).  Stage-wise bit-exact and end to end vs the C port."""
