@@ -789,6 +789,54 @@ def test_rpn_proposals_cfg2_full_size():
     assert np.all(props[:, :-1, 4] >= props[:, 1:, 4])           # sortedness of the truncated output
 
 
+def test_two_host_threads_on_two_streams_match_serial_results():
+    """include/mxdet.h: 're-entrant; concurrent calls on distinct streams / workspaces are safe'.  Two host threads, each on
+    its own stream (hence its own workspaces), interleave RoIAlign forward / backward and the proposal stage; every result
+    must equal the one computed serially (all three are bit-reproducible)."""
+    import threading
+    from mxdetection_b200.models.rpn_heads import ProposalConfig, RPNHead
+    from mxdetection_b200.ops import roi_align_fpn_forward, roi_align_fpn_backward
+    d = syn.cfg3(batch=2)
+    feats = [T(f) for f in d["feats"]]; rois = T(d["rois"]); gout = T(d["grad_out"])
+    shapes = [f.shape for f in d["feats"]]
+    r = syn.rpn_inputs(31, 2, 800, 1088)
+    sc = [T(x) for x in r["scores"]]; dl = [T(x) for x in r["deltas"]]; shp = T(r["img_shapes"])
+    cfg = ProposalConfig(nms_pre=2000, nms_post=1000, max_num=1000, nms_thr=0.7)
+    ref_out = roi_align_fpn_forward(feats, rois, (7, 7), d["scales"], 2).clone()
+    ref_g = [t.clone() for t in roi_align_fpn_backward(gout, rois, shapes, (7, 7), d["scales"], 2)]
+    ref_p, ref_n = [t.clone() for t in RPNHead().get_proposals(sc, dl, r["feat_shapes"], shp, cfg)]
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(order):
+        try:
+            st = torch.cuda.Stream()
+            head = RPNHead()
+            with torch.cuda.stream(st):
+                for it in range(6):
+                    for what in order:
+                        if what == "f":
+                            ok = torch.equal(roi_align_fpn_forward(feats, rois, (7, 7), d["scales"], 2), ref_out)
+                        elif what == "b":
+                            g = roi_align_fpn_backward(gout, rois, shapes, (7, 7), d["scales"], 2)
+                            ok = all(torch.equal(a, b) for a, b in zip(g, ref_g))
+                        else:
+                            p, n = head.get_proposals(sc, dl, r["feat_shapes"], shp, cfg)
+                            ok = torch.equal(p, ref_p) and torch.equal(n, ref_n)
+                        if not ok:
+                            errors.append("thread %s iteration %d: %s differs" % (order, it, what))
+                st.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(o,)) for o in ("fbp", "pbf")]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+
+
 def test_rpn_proposals_and_assigner_repeatable_bit_for_bit():
     """The latency-bound stages use shared-memory atomics for compaction and per-GT maxima; their RESULTS must not depend
     on arrival order: 25 back-to-back launches of the config-5-shard proposal stage (8 images, 4-CTA clusters) and of
