@@ -1099,6 +1099,60 @@ def test_pipeline_is_cuda_graph_capturable():
     assert torch.equal(props, eager)
 
 
+def test_roi_align_many_images_many_rois(roi_path):
+    """Unit / group / tile bookkeeping far from the benchmark's shape: 24 images, 6000 RoIs in RANDOM batch order (a
+    tile's RoI list then spans the whole RoI array: several bitmap windows in the list sort), 3 levels, 32 channels."""
+    from mxdetection_b200.ops import roi_align_fpn_forward, roi_align_fpn_backward
+    rng = np.random.default_rng(77)
+    Nn, C, R = 24, 32, 6000
+    shapes = [(Nn, C, 64, 96), (Nn, C, 32, 48), (Nn, C, 16, 24)]
+    scales = [0.25, 0.125, 0.0625]
+    feats = [rng.standard_normal(sh).astype(F) for sh in shapes]
+    rois = np.concatenate([rng.integers(0, Nn, (R, 1)), syn.gt_boxes(rng, 256, 384, R)], 1).astype(F)
+    lv = oracle.map_roi_levels(rois, 3)
+    out = roi_align_fpn_forward([T(f) for f in feats], T(rois), (7, 7), scales, 2)
+    assert close(N(out), cref.roi_align_forward(feats, rois, (7, 7), scales, 2, lv), 1e-5)
+    gout = rng.standard_normal((R, C, 7, 7)).astype(F)
+    g = roi_align_fpn_backward(T(gout), T(rois), shapes, (7, 7), scales, 2)
+    gref = cref.roi_align_backward(gout, rois, shapes, (7, 7), scales, 2, lv)
+    assert all(close(N(a), b, 1e-4) for a, b in zip(g, gref))
+    g2 = roi_align_fpn_backward(T(gout), T(rois), shapes, (7, 7), scales, 2)
+    if roi_path != "gather":
+        assert all(torch.equal(a, b) for a, b in zip(g, g2))        # list order fixed -> bit-reproducible
+
+
+def test_roi_stage_is_cuda_graph_capturable():
+    """The FPN RoI stage of the benchmarked kind (row-ring forward with tensor-map TMA, tile backward, programmatic
+    dependent launches between planners and main kernels) captures into a CUDA graph and replays bit-identically."""
+    from mxdetection_b200.ops import roi_align_fpn_forward, roi_align_fpn_backward
+    d = syn.cfg3(batch=4, with_features=False)          # 4 images: enough units for the ring forward
+    shapes = [(4, 256, h, w) for h, w in d["feat_shapes"]]
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    feats = [torch.randn(s, device="cuda", generator=gen) for s in shapes]
+    rois = T(d["rois"])
+    gout = torch.randn((rois.shape[0], 256, 7, 7), device="cuda", generator=gen)
+    out = torch.empty_like(gout)
+    grads = [torch.empty(s, device="cuda") for s in shapes]
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(st):
+        roi_align_fpn_forward(feats, rois, (7, 7), d["scales"], 2, out=out)
+        roi_align_fpn_backward(gout, rois, shapes, (7, 7), d["scales"], 2, grad_feats=grads)
+        st.synchronize()
+        eager_out, eager_g = out.clone(), [t.clone() for t in grads]
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            roi_align_fpn_forward(feats, rois, (7, 7), d["scales"], 2, out=out)
+            roi_align_fpn_backward(gout, rois, shapes, (7, 7), d["scales"], 2, grad_feats=grads)
+        for _ in range(3):
+            out.fill_(float("nan"))
+            for t in grads:
+                t.fill_(float("nan"))
+            g.replay()
+            st.synchronize()
+            assert torch.equal(out, eager_out) and all(torch.equal(a, b) for a, b in zip(grads, eager_g))
+
+
 # ============================================================ SURVEY 8(e): tail gather ==
 def test_pack_detections_layout():
     from mxdetection_b200.parallel import pack_detections, unpack_detections
