@@ -52,3 +52,38 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def workspace_canaries(request):
+    """Every GPU test runs with guarded workspaces (compute-sanitizer is not available on the GPU pool): the scratch buffer the
+    Python mirror hands to the library sits between two 4 KiB guard zones filled with a pattern, the library is told the
+    exact size its own *_workspace_bytes query asked for, and after the test both zones must be untouched - a kernel that
+    writes before or past its workspace fails the test that triggered it."""
+    if "gpu" not in request.keywords:
+        yield
+        return
+    import torch
+    from mxdetection_b200 import _lib as L
+    guard, pattern = 4096, 0xA5
+    pool = {}
+    orig = L.workspace
+
+    def canary_workspace(nbytes, device, tag):
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream, tag)
+        n = max(int(nbytes), 256)
+        ent = pool.get(key)
+        if ent is None or ent[1] < n:
+            ent = (torch.full((n + 2 * guard,), pattern, dtype=torch.uint8, device=device), n)
+            pool[key] = ent
+        return ent[0][guard:guard + ent[1]]
+
+    L.workspace = canary_workspace
+    try:
+        yield
+    finally:
+        L.workspace = orig
+    torch.cuda.synchronize()
+    for key, (full, n) in pool.items():
+        ok = bool((full[:guard] == pattern).all()) and bool((full[guard + n:] == pattern).all())
+        assert ok, "workspace %r (%d bytes): a kernel wrote outside the size its *_workspace_bytes query reported" % (key, n)
