@@ -1099,6 +1099,33 @@ def test_pipeline_is_cuda_graph_capturable():
     assert torch.equal(props, eager)
 
 
+def test_roi_stage_writes_exactly_its_outputs():
+    """Output-side canaries: `out` and every gradient map are views into larger buffers whose guard zones (64 KiB either
+    side, a NaN pattern) must survive the row-ring forward and the tile backward, and every byte in between is written."""
+    from mxdetection_b200.ops import roi_align_fpn_forward, roi_align_fpn_backward
+    d = syn.cfg3(batch=4, with_features=False)
+    shapes = [(4, 256, h, w) for h, w in d["feat_shapes"]]
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    feats = [torch.randn(s, device="cuda", generator=gen) for s in shapes]
+    rois = T(d["rois"])
+    gout = torch.randn((rois.shape[0], 256, 7, 7), device="cuda", generator=gen)
+    G = 16384                                                  # guard floats
+
+    def guarded(shape):
+        n = int(np.prod(shape))
+        full = torch.full((n + 2 * G,), float("nan"), device="cuda")
+        return full, full[G:G + n].view(shape)
+
+    f_out, out = guarded(tuple(gout.shape))
+    gs = [guarded(s) for s in shapes]
+    roi_align_fpn_forward(feats, rois, (7, 7), d["scales"], 2, out=out)
+    roi_align_fpn_backward(gout, rois, shapes, (7, 7), d["scales"], 2, grad_feats=[v for _, v in gs])
+    torch.cuda.synchronize()
+    for full, view in [(f_out, out)] + gs:
+        assert bool(torch.isnan(full[:G]).all()) and bool(torch.isnan(full[-G:]).all()), "wrote outside the output tensor"
+        assert not bool(torch.isnan(view).any()), "left output bytes unwritten"
+
+
 def test_roi_align_many_images_many_rois(roi_path):
     """Unit / group / tile bookkeeping far from the benchmark's shape: 24 images, 6000 RoIs in RANDOM batch order (a
     tile's RoI list then spans the whole RoI array: several bitmap windows in the list sort), 3 levels, 32 channels."""
