@@ -54,7 +54,7 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-CURRENT_NCU_SUMMARY = "ncu_r2e.txt"     # `ncu --set full` capture of the kernels this tree ships (profiles/README.md)
+CURRENT_NCU_SUMMARY = "ncu_r2f.txt"     # `ncu --set full` capture of the kernels this tree ships (profiles/README.md)
 
 
 def bind_to_gpu_numa_node(index):
