@@ -568,7 +568,8 @@ __device__ __forceinline__ bool tb_h(const float* __restrict__ gl, const uint2* 
 // The packed bin {w1, w2, w3, 4 column bytes} is fetched and unpacked once for both rows.  (Skipping the slots that
 // point at the trash column - 19 % of them on the benchmark workload - with warp-uniform branches measured 5 %
 // SLOWER: 0.437 vs 0.414 ms; the straight-line bin body schedules better than it saves.  Predicating them off in
-// inline PTX (@p ld / fma / st.shared, no branch) changed nothing: 0.407 vs 0.405 ms.  A 32-byte bin entry with w0 and
+// inline PTX (@p ld / fma / st.shared, no branch) changed nothing: 0.407 vs 0.405 ms - a predicated-off LDS / STS
+// occupies the LSU pipe exactly like a predicated-on one (profiles/microbench/pred_lds.cu: 2.02 vs 2.04 cycles).  A 32-byte bin entry with w0 and
 // the four byte offsets ready to use - 18 instead of 26 instructions per bin, but a second uniform LDS.128 - was 3 %
 // SLOWER (0.417 ms): the kernel sits at 82 % of the LSU data pipe's wavefront rate, so a shared-memory wavefront is
 // worth more than eight ALU instructions here.)
